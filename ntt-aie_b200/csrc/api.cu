@@ -1,0 +1,358 @@
+// api.cu -- the C ABI of libnttb200.so (include/nttb200.h): plan management, the
+// dispatch between the fused and the generic kernels, the host-buffer pipeline.
+//
+// This file is the successor of the reference host harness around one launch
+// (src/test.cpp:110-190): load device image + allocate/sync buffer objects ->
+// nttb200_plan_create; kernel(bo_inA, bo_root, bo_outC) + run.wait() ->
+// nttb200_gs_batch / nttb200_gs_host.  There is no CPU compute path in here:
+// without a usable CUDA device every compute entry point returns an error.
+#include <stdio.h>
+#include <string.h>
+
+#include <new>
+#include <vector>
+
+#include "plan.h"
+
+namespace nttb200 {
+
+std::atomic<uint64_t> g_launches{0};
+static thread_local char t_err[512] = "";
+
+int cuda_fail(cudaError_t e, const char *what) {
+    snprintf(t_err, sizeof(t_err), "%s: %s (%s)", what, cudaGetErrorName(e),
+             cudaGetErrorString(e));
+    cudaGetLastError();  // clear the sticky-free error state
+    return e == cudaErrorNoDevice || e == cudaErrorInvalidDevice ||
+                   e == cudaErrorInsufficientDriver
+               ? NTTB200_ERR_NO_DEVICE
+               : NTTB200_ERR_CUDA;
+}
+
+static uint64_t powmod64(uint64_t b, uint64_t e, uint64_t m) {
+    uint64_t r = 1 % m;
+    b %= m;
+    while (e) {
+        if (e & 1) r = (unsigned __int128) r * b % m;
+        b = (unsigned __int128) b * b % m;
+        e >>= 1;
+    }
+    return r;
+}
+
+static uint32_t shoup_companion(uint32_t w, uint32_t q) {
+    return (uint32_t) (((uint64_t) w << 32) / q);
+}
+
+struct DeviceGuard {
+    int prev = -1;
+    bool ok = false;
+    explicit DeviceGuard(int dev) {
+        if (cudaGetDevice(&prev) != cudaSuccess) prev = -1;
+        ok = cudaSetDevice(dev) == cudaSuccess;
+    }
+    ~DeviceGuard() {
+        if (prev >= 0) cudaSetDevice(prev);
+    }
+};
+
+static bool full_depth(const nttb200_plan *p, int stage_limit) {
+    return stage_limit < 0 || stage_limit > (int) p->logn - 2;
+}
+
+}  // namespace nttb200
+
+using namespace nttb200;
+
+extern "C" {
+
+/* ---------------------------------------------------------------- tables */
+int nttb200_make_roots(int32_t n, int32_t *roots, int32_t p, int32_t g) {
+    if (!roots || n < 1 || p < 2 || p > (1 << 30) || g < 0) return NTTB200_ERR_INVALID_ARG;
+    // src/test.cpp:137-139 (roots[0] = 1) and :27-32 (w = g^((p-1)/n), running product)
+    uint64_t w = powmod64((uint64_t) g, (uint64_t) ((p - 1) / n), (uint64_t) p);
+    roots[0] = 1;
+    uint64_t cur = 1;
+    for (int32_t i = 1; i < n; i++) {
+        cur = cur * w % (uint64_t) p;
+        roots[i] = (int32_t) cur;
+    }
+    return NTTB200_OK;
+}
+
+int nttb200_make_bitrev_table(int32_t n, int32_t *table, int32_t p, int32_t base) {
+    if (!table || n < 1 || (n & (n - 1)) || p < 2 || p > (1 << 30) || base < 0) {
+        return NTTB200_ERR_INVALID_ARG;
+    }
+    int logn = 0;
+    while ((1 << logn) < n) logn++;
+    uint64_t cur = 1 % (uint64_t) p;
+    for (int32_t i = 0; i < n; i++) {
+        uint32_t r = 0;
+        for (int b = 0; b < logn; b++) r |= ((uint32_t) (i >> b) & 1u) << (logn - 1 - b);
+        table[r] = (int32_t) cur;  // table[bitrev(i)] = base^i  <=>  table[k] = base^bitrev(k)
+        cur = cur * (uint64_t) base % (uint64_t) p;
+    }
+    return NTTB200_OK;
+}
+
+int32_t nttb200_powmod(int32_t b, int64_t e, int32_t m) {
+    if (m < 1 || e < 0 || b < 0) return -1;
+    return (int32_t) powmod64((uint64_t) b, (uint64_t) e, (uint64_t) m);
+}
+
+/* ------------------------------------------------------------------ plan */
+int nttb200_plan_create(nttb200_plan **out, int device, uint32_t logn, uint32_t q,
+                        const int32_t *table_host, uint32_t flags) {
+    if (!out) return NTTB200_ERR_INVALID_ARG;
+    *out = nullptr;
+    if (!table_host || logn < 1 || logn > NTTB200_MAX_LOGN) return NTTB200_ERR_INVALID_ARG;
+    if (flags & ~(NTTB200_ORDER_AIE_DEVICE | NTTB200_FORCE_GENERIC)) return NTTB200_ERR_INVALID_ARG;
+    if ((flags & NTTB200_ORDER_AIE_DEVICE) && logn < 4) return NTTB200_ERR_INVALID_ARG;
+    if (q < 2 || q > (1u << 30)) return NTTB200_ERR_MODULUS;
+    const uint32_t n = 1u << logn;
+    for (uint32_t i = 1; i < n; i++) {  // table[0] is never read (src/test.cpp:45: h >= 1)
+        if (table_host[i] < 0 || (uint32_t) table_host[i] >= q) return NTTB200_ERR_TABLE;
+    }
+    int count = 0;
+    cudaError_t e = cudaGetDeviceCount(&count);
+    if (e != cudaSuccess) return cuda_fail(e, "cudaGetDeviceCount");
+    if (count == 0 || device < 0 || device >= count) {
+        snprintf(t_err, sizeof(t_err), "device %d not available (%d CUDA devices)", device, count);
+        return NTTB200_ERR_NO_DEVICE;
+    }
+    DeviceGuard guard(device);
+    if (!guard.ok) return cuda_fail(cudaGetLastError(), "cudaSetDevice");
+
+    nttb200_plan *p = new (std::nothrow) nttb200_plan();
+    if (!p) return NTTB200_ERR_ALLOC;
+    p->device = device;
+    p->logn = logn;
+    p->n = n;
+    p->q = q;
+    p->flags = flags;
+    p->mu = (uint64_t) ((((unsigned __int128) 1) << 62) / q);
+    cudaDeviceGetAttribute(&p->sm_count, cudaDevAttrMultiProcessorCount, device);
+    // N^-1 mod q exists iff q is odd; found by the extended Euclid-free route
+    // n_inv = ((q+1)/2)^logn, valid for every odd q (prime or not)
+    if (q & 1u) {
+        p->n_inv = (uint32_t) powmod64((uint64_t) (q + 1) / 2, logn, q);
+        p->n_inv_shoup = shoup_companion(p->n_inv, q);
+    }
+
+    std::vector<uint2> tw;
+    try {
+        tw.resize(n);
+    } catch (...) {
+        delete p;
+        return NTTB200_ERR_ALLOC;
+    }
+    tw[0] = make_uint2(0, 0);
+    for (uint32_t i = 1; i < n; i++) {
+        uint32_t w = (uint32_t) table_host[i];
+        tw[i] = make_uint2(w, shoup_companion(w, q));
+    }
+    e = cudaMalloc(&p->d_tw, sizeof(uint2) * (size_t) n);
+    if (e != cudaSuccess) {
+        delete p;
+        return e == cudaErrorMemoryAllocation ? NTTB200_ERR_ALLOC : cuda_fail(e, "cudaMalloc(table)");
+    }
+    e = cudaMemcpy(p->d_tw, tw.data(), sizeof(uint2) * (size_t) n, cudaMemcpyHostToDevice);
+    if (e != cudaSuccess) {
+        cudaFree(p->d_tw);
+        delete p;
+        return cuda_fail(e, "cudaMemcpy(table)");
+    }
+    if (!(flags & NTTB200_FORCE_GENERIC)) {
+        int rc = fused_prepare(p);
+        if (rc != NTTB200_OK && rc != NTTB200_ERR_UNSUPPORTED) {
+            cudaFree(p->d_tw);
+            delete p;
+            return rc;
+        }
+    }
+    *out = p;
+    return NTTB200_OK;
+}
+
+int nttb200_plan_destroy(nttb200_plan *p) {
+    if (!p) return NTTB200_OK;
+    DeviceGuard guard(p->device);
+    if (p->host_ready) {
+        for (int k = 0; k < kHostStreams; k++) {
+            if (p->hstream[k]) cudaStreamSynchronize(p->hstream[k]);
+            if (p->d_stage[k]) cudaFree(p->d_stage[k]);
+            if (p->hevent[k]) cudaEventDestroy(p->hevent[k]);
+            if (p->hstream[k]) cudaStreamDestroy(p->hstream[k]);
+        }
+    }
+    fused_release(p);
+    if (p->d_tw) cudaFree(p->d_tw);
+    delete p;
+    return NTTB200_OK;
+}
+
+/* -------------------------------------------------------------- hot path */
+static int run_gs(nttb200_plan *p, const int32_t *d_in, int32_t *d_out, size_t batch,
+                  int stage_limit, cudaStream_t st) {
+    const bool full = full_depth(p, stage_limit);
+    const bool permute = full && (p->flags & NTTB200_ORDER_AIE_DEVICE);
+    if (full && !(p->flags & NTTB200_FORCE_GENERIC)) {
+        int rc = launch_fused_gs(p, d_in, d_out, batch, permute, st);
+        if (rc != NTTB200_ERR_UNSUPPORTED) return rc;
+    }
+    p->last_path = "generic_stage_pass";
+    int se = full ? (int) p->logn : stage_limit + 1;
+    return launch_generic(p, d_in, d_out, batch, 0, se, /*ct=*/false, permute, st);
+}
+
+int nttb200_gs_batch(nttb200_plan *p, const int32_t *d_in, int32_t *d_out, size_t batch,
+                     int stage_limit, void *stream) {
+    if (!p || (batch && (!d_in || !d_out))) return NTTB200_ERR_INVALID_ARG;
+    DeviceGuard guard(p->device);
+    return run_gs(p, d_in, d_out, batch, stage_limit, (cudaStream_t) stream);
+}
+
+int nttb200_ct_batch(nttb200_plan *p, const int32_t *d_in, int32_t *d_out, size_t batch,
+                     int stage_limit, void *stream) {
+    if (!p || (batch && (!d_in || !d_out))) return NTTB200_ERR_INVALID_ARG;
+    DeviceGuard guard(p->device);
+    // CT stage idx (0 = stride N/2) acts on index bit logn-1-idx
+    const bool full = full_depth(p, stage_limit);
+    int sb = full ? 0 : (int) p->logn - 1 - stage_limit;
+    p->last_path = "generic_stage_pass";
+    return launch_generic(p, d_in, d_out, batch, sb, (int) p->logn, /*ct=*/true, false,
+                          (cudaStream_t) stream);
+}
+
+int nttb200_gs_stage_range(nttb200_plan *p, const int32_t *d_in, int32_t *d_out, size_t batch,
+                           int stage_begin, int stage_end, void *stream) {
+    if (!p || (batch && (!d_in || !d_out))) return NTTB200_ERR_INVALID_ARG;
+    if (stage_begin < 0 || stage_end > (int) p->logn || stage_begin > stage_end) {
+        return NTTB200_ERR_INVALID_ARG;
+    }
+    DeviceGuard guard(p->device);
+    if (stage_begin == stage_end) {
+        if (d_in != d_out && batch) {
+            NTTB200_CUDA(cudaMemcpyAsync(d_out, d_in, sizeof(int32_t) * batch * p->n,
+                                         cudaMemcpyDeviceToDevice, (cudaStream_t) stream));
+        }
+        return NTTB200_OK;
+    }
+    p->last_path = "generic_stage_pass";
+    return launch_generic(p, d_in, d_out, batch, stage_begin, stage_end, false, false,
+                          (cudaStream_t) stream);
+}
+
+static int host_prepare(nttb200_plan *p) {
+    if (p->host_ready) return NTTB200_OK;
+    // staging buffers of ~16 MiB each: deep enough to hide the PCIe latency,
+    // small enough that the first kernel starts early
+    size_t polys = ((size_t) 16 << 20) / (sizeof(int32_t) * p->n);
+    if (polys < 1) polys = 1;
+    for (int k = 0; k < kHostStreams; k++) {
+        NTTB200_CUDA(cudaStreamCreateWithFlags(&p->hstream[k], cudaStreamNonBlocking));
+        NTTB200_CUDA(cudaEventCreateWithFlags(&p->hevent[k], cudaEventDisableTiming));
+        NTTB200_CUDA(cudaMalloc(&p->d_stage[k], sizeof(int32_t) * polys * p->n));
+    }
+    p->stage_polys = polys;
+    p->host_ready = true;
+    return NTTB200_OK;
+}
+
+int nttb200_gs_host(nttb200_plan *p, const int32_t *h_in, int32_t *h_out, size_t batch,
+                    int stage_limit) {
+    if (!p || (batch && (!h_in || !h_out))) return NTTB200_ERR_INVALID_ARG;
+    DeviceGuard guard(p->device);
+    std::lock_guard<std::mutex> lock(p->host_mu);
+    int rc = host_prepare(p);
+    if (rc != NTTB200_OK) return rc;
+    const size_t n = p->n;
+    size_t done = 0;
+    int k = 0;
+    while (done < batch) {
+        size_t polys = batch - done < p->stage_polys ? batch - done : p->stage_polys;
+        cudaStream_t st = p->hstream[k];
+        int32_t *d = p->d_stage[k];
+        // the stream is ordered: the previous D2H of this staging buffer has been
+        // queued before this H2D, so the buffer is reused safely
+        NTTB200_CUDA(cudaMemcpyAsync(d, h_in + done * n, sizeof(int32_t) * polys * n,
+                                     cudaMemcpyHostToDevice, st));
+        rc = run_gs(p, d, d, polys, stage_limit, st);
+        if (rc != NTTB200_OK) return rc;
+        NTTB200_CUDA(cudaMemcpyAsync(h_out + done * n, d, sizeof(int32_t) * polys * n,
+                                     cudaMemcpyDeviceToHost, st));
+        done += polys;
+        k = (k + 1) % kHostStreams;
+    }
+    for (int s = 0; s < kHostStreams; s++) {
+        NTTB200_CUDA(cudaStreamSynchronize(p->hstream[s]));
+    }
+    return NTTB200_OK;
+}
+
+/* ---------------------------------------------------- multiplier operators */
+int nttb200_pointwise(nttb200_plan *p, const int32_t *d_a, const int32_t *d_b, int32_t *d_c,
+                      size_t count, void *stream) {
+    if (!p || (count && (!d_a || !d_b || !d_c))) return NTTB200_ERR_INVALID_ARG;
+    DeviceGuard guard(p->device);
+    return launch_pointwise(p, d_a, d_b, d_c, count, (cudaStream_t) stream);
+}
+
+int nttb200_scale(nttb200_plan *p, const int32_t *d_a, int32_t *d_c, size_t count, int32_t scalar,
+                  void *stream) {
+    if (!p || (count && (!d_a || !d_c))) return NTTB200_ERR_INVALID_ARG;
+    if (scalar < 0 || (uint32_t) scalar >= p->q) return NTTB200_ERR_INVALID_ARG;
+    DeviceGuard guard(p->device);
+    return launch_scale(p, d_a, d_c, count, (uint32_t) scalar,
+                        shoup_companion((uint32_t) scalar, p->q), (cudaStream_t) stream);
+}
+
+int nttb200_polymul_negacyclic(nttb200_plan *fwd, nttb200_plan *inv, const int32_t *d_a,
+                               const int32_t *d_b, int32_t *d_c, size_t batch, void *stream) {
+    if (!fwd || !inv || (batch && (!d_a || !d_b || !d_c))) return NTTB200_ERR_INVALID_ARG;
+    if (fwd->logn != inv->logn || fwd->q != inv->q || fwd->device != inv->device) {
+        return NTTB200_ERR_INVALID_ARG;
+    }
+    if (!(fwd->q & 1u)) return NTTB200_ERR_MODULUS;  // N^-1 must exist
+    if ((fwd->flags | inv->flags) & NTTB200_ORDER_AIE_DEVICE) return NTTB200_ERR_INVALID_ARG;
+    if (batch == 0) return NTTB200_OK;
+    DeviceGuard guard(fwd->device);
+    cudaStream_t st = (cudaStream_t) stream;
+    const size_t words = batch * fwd->n;
+    // scratch for NTT(b) (and NTT(a) when the output aliases b)
+    int32_t *tmp = nullptr;
+    NTTB200_CUDA(cudaMallocAsync(&tmp, sizeof(int32_t) * words, st));
+    int rc = launch_generic(fwd, d_b, tmp, batch, 0, (int) fwd->logn, true, false, st);
+    if (rc == NTTB200_OK) rc = launch_generic(fwd, d_a, d_c, batch, 0, (int) fwd->logn, true, false, st);
+    if (rc == NTTB200_OK) rc = launch_pointwise(fwd, d_c, tmp, d_c, words, st);
+    if (rc == NTTB200_OK) rc = run_gs(inv, d_c, d_c, batch, -1, st);
+    if (rc == NTTB200_OK) rc = launch_scale(inv, d_c, d_c, words, inv->n_inv, inv->n_inv_shoup, st);
+    cudaError_t e = cudaFreeAsync(tmp, st);
+    if (rc == NTTB200_OK && e != cudaSuccess) rc = cuda_fail(e, "cudaFreeAsync");
+    return rc;
+}
+
+/* ---------------------------------------------------------- introspection */
+const char *nttb200_strerror(int status) {
+    switch (status) {
+        case NTTB200_OK: return "ok";
+        case NTTB200_ERR_INVALID_ARG: return "invalid argument";
+        case NTTB200_ERR_MODULUS: return "modulus outside [2, 2^30] (or even where N^-1 is needed)";
+        case NTTB200_ERR_TABLE: return "twiddle table entry outside [0, q)";
+        case NTTB200_ERR_CUDA: return "CUDA error (see nttb200_last_error)";
+        case NTTB200_ERR_NO_DEVICE: return "no usable CUDA device; this library has no CPU path";
+        case NTTB200_ERR_ALLOC: return "allocation failed";
+        case NTTB200_ERR_UNSUPPORTED: return "unsupported configuration";
+        default: return "unknown status";
+    }
+}
+
+const char *nttb200_last_error(void) { return t_err; }
+uint64_t nttb200_kernel_launches(void) { return g_launches.load(std::memory_order_relaxed); }
+const char *nttb200_plan_last_path(const nttb200_plan *p) { return p ? p->last_path : "none"; }
+uint32_t nttb200_plan_logn(const nttb200_plan *p) { return p ? p->logn : 0; }
+uint32_t nttb200_plan_modulus(const nttb200_plan *p) { return p ? p->q : 0; }
+const char *nttb200_version(void) { return "nttb200 0.1 (sm_100a)"; }
+
+}  // extern "C"

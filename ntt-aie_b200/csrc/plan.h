@@ -1,0 +1,81 @@
+// plan.h -- internal plan object and kernel launch interfaces (not installed).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <atomic>
+#include <mutex>
+
+#include "../../include/nttb200.h"
+
+namespace nttb200 {
+
+constexpr int kHostStreams = 4;  // chunk pipeline depth of nttb200_gs_host
+
+// Uniform twiddles of the strided (second) round of the fused kernels: stage s of
+// that round uses 2^(R2-1-k) table entries that depend only on the register index,
+// never on the thread or the polynomial, so they travel as kernel parameters
+// (constant bank operands of IMAD) -- 63 (w, w') pairs at most.
+struct UniformTw {
+    uint32_t w[64];
+    uint32_t wp[64];
+};
+
+}  // namespace nttb200
+
+struct nttb200_plan {
+    int device = 0;
+    uint32_t logn = 0;
+    uint32_t n = 0;
+    uint32_t q = 0;
+    uint32_t flags = 0;
+    uint64_t mu = 0;         // floor(2^62 / q) for barrett_mul
+    uint32_t n_inv = 0;      // N^-1 mod q (0 if it does not exist)
+    uint32_t n_inv_shoup = 0;
+    uint2 *d_tw = nullptr;   // [N] (w, floor(w*2^32/q)), golden index rule table[h+i]
+    // fused-kernel twiddle staging (built lazily per kernel family)
+    uint4 *d_tw_r1 = nullptr;        // round-1 per-thread twiddles, kernel-private order
+    nttb200::UniformTw uni_gs{};     // round-2 uniform twiddles, GS network
+    int sm_count = 148;
+    const char *last_path = "none";
+
+    // nttb200_gs_host resources (lazily created, guarded by host_mu)
+    std::mutex host_mu;
+    cudaStream_t hstream[nttb200::kHostStreams] = {};
+    cudaEvent_t hevent[nttb200::kHostStreams] = {};
+    int32_t *d_stage[nttb200::kHostStreams] = {};
+    size_t stage_polys = 0;  // capacity of each staging buffer in polynomials
+    bool host_ready = false;
+};
+
+namespace nttb200 {
+
+extern std::atomic<uint64_t> g_launches;
+
+// error plumbing (api.cu)
+int cuda_fail(cudaError_t e, const char *what);
+#define NTTB200_CUDA(call)                                        \
+    do {                                                          \
+        cudaError_t e__ = (call);                                 \
+        if (e__ != cudaSuccess) return ::nttb200::cuda_fail(e__, #call); \
+    } while (0)
+
+// generic stage-pass kernels (kernels_generic.cu): stages [sb, se) of the GS
+// (ascending stride) or CT (descending stride) network; permute_out applies the
+// ans_order block permutation on the last pass's store.
+int launch_generic(nttb200_plan *p, const int32_t *d_in, int32_t *d_out, size_t batch, int sb,
+                   int se, bool ct, bool permute_out, cudaStream_t st);
+int launch_pointwise(nttb200_plan *p, const int32_t *a, const int32_t *b, int32_t *c, size_t count,
+                     cudaStream_t st);
+int launch_scale(nttb200_plan *p, const int32_t *a, int32_t *c, size_t count, uint32_t s,
+                 uint32_t s_shoup, cudaStream_t st);
+
+// fused register-radix kernels (kernels_fused.cu).  Return NTTB200_ERR_UNSUPPORTED
+// when the (logn, options) combination has no fused kernel so the caller can fall
+// back to the generic passes (still CUDA -- never a CPU path).
+int fused_prepare(nttb200_plan *p);
+void fused_release(nttb200_plan *p);
+int launch_fused_gs(nttb200_plan *p, const int32_t *d_in, int32_t *d_out, size_t batch,
+                    bool permute_out, cudaStream_t st);
+
+}  // namespace nttb200
