@@ -1,0 +1,255 @@
+"""GPU parity tests: the CUDA path (through the C ABI) against the oracle and the
+committed golden fixtures.  Bit-exact: every comparison is integer equality."""
+import numpy as np
+import pytest
+import torch
+
+from conftest import Q29, Q30, load_golden
+
+pytestmark = pytest.mark.gpu
+
+
+def dev(a):
+    return torch.from_numpy(np.ascontiguousarray(a, dtype=np.int32)).cuda()
+
+
+def run_gs(lib, a, roots, p, stage=-1, flags=0, inplace=False):
+    a = np.ascontiguousarray(a, dtype=np.int32)
+    n = a.shape[-1]
+    batch = a.size // n
+    d_in = dev(a)
+    d_out = d_in if inplace else torch.empty_like(d_in)
+    with lib.Plan(n.bit_length() - 1, p, roots, flags=flags) as plan:
+        plan.gs(d_in, d_out, batch, stage)
+        torch.cuda.synchronize()
+        path = plan.last_path
+    return d_out.cpu().numpy(), path
+
+
+@pytest.fixture(scope="module", autouse=True)
+def _need_gpu():
+    assert torch.cuda.is_available(), "gpu-marked tests need a CUDA device"
+
+
+def test_library_is_loaded_and_counts_launches(lib):
+    before = lib.kernel_launches()
+    g = load_golden("default_n2048_p3329.npz")
+    out, _ = run_gs(lib, g["a"], g["roots"], int(g["p"]), 10)
+    assert np.array_equal(out, g["out"])
+    assert lib.kernel_launches() > before
+
+
+@pytest.mark.parametrize("flags", [0, 2])
+def test_reference_default_config(lib, flags):
+    """N=2048, p=3329, g=3, a[i]=i, full depth == golden (src/test.cpp:203-235)."""
+    g = load_golden("default_n2048_p3329.npz")
+    roots = lib.make_roots(2048, 3329, 3)
+    assert np.array_equal(roots, g["roots"])
+    out, _ = run_gs(lib, g["a"], roots, 3329, 10, flags=flags)
+    assert np.array_equal(out, g["out"])
+
+
+def test_reference_default_config_device_order(lib, oracle_mod):
+    """ORDER_AIE_DEVICE reproduces what the AIE leaves in bo_outC: the golden permuted
+    by ans_order (src/test.cpp:69-71,212-219)."""
+    g = load_golden("default_n2048_p3329.npz")
+    for flags in (1, 3):
+        out, _ = run_gs(lib, g["a"], g["roots"], 3329, 10, flags=flags)
+        assert np.array_equal(out, oracle_mod.ans_order_permute(g["out"]))
+        out, _ = run_gs(lib, g["a"], g["roots"], 3329, 10, flags=flags, inplace=True)
+        assert np.array_equal(out, oracle_mod.ans_order_permute(g["out"]))
+
+
+def test_stage_early_exit(lib, oracle_mod):
+    """Every partial depth of the default config (src/test.cpp:55-58)."""
+    g = load_golden("default_n2048_p3329.npz")
+    for s in range(11):
+        out, _ = run_gs(lib, g["a"], g["roots"], 3329, s)
+        assert np.uint64(oracle_mod.fnv1a64_words(out)) == g["stage_digest"][s], f"stage {s}"
+
+
+@pytest.mark.parametrize("name", ["n4096_q29.npz", "n4096_p3329.npz"])
+@pytest.mark.parametrize("flags", [0, 2])
+def test_n4096_fixtures(lib, name, flags):
+    g = load_golden(name)
+    out, _ = run_gs(lib, g["a"], g["roots"], int(g["p"]), flags=flags)
+    assert np.array_equal(out, g["out"])
+
+
+def test_small_fixtures(lib):
+    g = load_golden("small.npz")
+    for logn in range(1, 7):
+        for p, tag in ((Q29, "q29"), (3329, "p3329")):
+            out, _ = run_gs(lib, g[f"a_{tag}_{logn}"], g[f"roots_{tag}_{logn}"], p)
+            assert np.array_equal(out, g[f"out_{tag}_{logn}"]), (logn, tag)
+
+
+def test_n65536_digest(lib, oracle_mod):
+    g = load_golden("n65536_q29_digest.npz")
+    n, p = int(g["n"]), int(g["p"])
+    a = np.random.default_rng(int(g["seed"])).integers(0, p, n, dtype=np.int32)
+    out, _ = run_gs(lib, a, lib.make_roots(n, p, 3), p)
+    assert np.uint64(oracle_mod.fnv1a64_words(out)) == g["digest"]
+    assert np.array_equal(out[:16], g["head"]) and np.array_equal(out[-16:], g["tail"])
+
+
+@pytest.mark.parametrize("logn", list(range(1, 17)))
+@pytest.mark.parametrize("flags", [0, 2])
+def test_gs_vs_oracle_all_sizes(lib, oracle_mod, logn, flags):
+    """N = 2..65536 x {reference w^i table, psi^-bitrev table, arbitrary table} x
+    {random, a[i]=i, all q-1, zeros}, ragged batch sizes."""
+    n = 1 << logn
+    rng = np.random.default_rng(1000 + logn)
+    for p in (Q29, 3329, Q30):
+        tables = [lib.make_roots(n, p, 3), rng.integers(0, p, n, dtype=np.int32)]
+        if p == Q29:
+            tables.append(lib.negacyclic_tables(n, p, 3)[1])
+        batch = 3 if logn > 12 else 5
+        a = rng.integers(0, p, (batch, n), dtype=np.int32)
+        a[0] = np.arange(n) % p
+        a[1] = p - 1
+        a[2] = 0
+        for table in tables:
+            out, _ = run_gs(lib, a, table, p, flags=flags)
+            assert np.array_equal(out, oracle_mod.ntt_gs(a, table, p)), (logn, p)
+
+
+@pytest.mark.parametrize("logn", [3, 7, 12, 14])
+def test_gs_partial_depth_and_inplace(lib, oracle_mod, logn):
+    n = 1 << logn
+    rng = np.random.default_rng(2000 + logn)
+    table = rng.integers(0, Q29, n, dtype=np.int32)
+    a = rng.integers(0, Q29, (4, n), dtype=np.int32)
+    for stage in (0, 1, logn // 2, logn - 2, logn - 1, logn + 5, -1):
+        out, _ = run_gs(lib, a, table, Q29, stage, inplace=(stage % 2 == 0))
+        assert np.array_equal(out, oracle_mod.ntt_gs(a, table, Q29, stage)), (logn, stage)
+
+
+@pytest.mark.parametrize("logn", [1, 4, 9, 12, 13, 16])
+def test_ct_vs_oracle(lib, oracle_mod, logn):
+    n = 1 << logn
+    rng = np.random.default_rng(3000 + logn)
+    fwd, inv = lib.negacyclic_tables(n, Q29, 3)
+    a = rng.integers(0, Q29, (3, n), dtype=np.int32)
+    d_in = dev(a)
+    d_out = torch.empty_like(d_in)
+    with lib.Plan(logn, Q29, fwd) as pf, lib.Plan(logn, Q29, inv) as pi:
+        for stage in (-1, 0, logn // 2):
+            pf.ct(d_in, d_out, 3, stage)
+            assert np.array_equal(d_out.cpu().numpy(), oracle_mod.ntt_ct(a, fwd, Q29, stage))
+        # round trip: GS(inv) o CT(fwd) = n * identity
+        pf.ct(d_in, d_out, 3)
+        pi.gs(d_out, d_out, 3)
+        assert np.array_equal(d_out.cpu().numpy(), oracle_mod.scale(a, n % Q29, Q29))
+
+
+def test_pointwise_and_scale(lib, oracle_mod):
+    rng = np.random.default_rng(5)
+    for p in (3329, Q29, Q30, 1 << 30, 2):
+        for count in (1, 3, 4, 1023, 4096 * 3 + 1):
+            a = rng.integers(0, p, count, dtype=np.int32)
+            b = rng.integers(0, p, count, dtype=np.int32)
+            a[0] = p - 1
+            b[0] = p - 1
+            with lib.Plan(4, p, np.zeros(16, np.int32)) as plan:
+                d_c = torch.empty(count, dtype=torch.int32, device="cuda")
+                plan.pointwise(dev(a), dev(b), d_c, count)
+                assert np.array_equal(d_c.cpu().numpy(), oracle_mod.pointwise(a, b, p))
+                s = int(rng.integers(0, p))
+                plan.scale(dev(a), d_c, count, s)
+                assert np.array_equal(d_c.cpu().numpy(), oracle_mod.scale(a, s, p))
+
+
+@pytest.mark.parametrize("logn", [1, 5, 8, 10])
+def test_polymul_vs_schoolbook(lib, oracle_mod, logn):
+    n = 1 << logn
+    rng = np.random.default_rng(6000 + logn)
+    fwd, inv = lib.negacyclic_tables(n, Q29, 3)
+    a = rng.integers(0, Q29, (3, n), dtype=np.int32)
+    b = rng.integers(0, Q29, (3, n), dtype=np.int32)
+    want = np.stack([oracle_mod.negacyclic_schoolbook(x, y, Q29) for x, y in zip(a, b)])
+    with lib.Plan(logn, Q29, fwd) as pf, lib.Plan(logn, Q29, inv) as pi:
+        d_a, d_b = dev(a), dev(b)
+        d_c = torch.empty_like(d_a)
+        lib.polymul_negacyclic(pf, pi, d_a, d_b, d_c, 3)
+        assert np.array_equal(d_c.cpu().numpy(), want)
+        assert np.array_equal(d_a.cpu().numpy(), a) and np.array_equal(d_b.cpu().numpy(), b)
+        lib.polymul_negacyclic(pf, pi, d_a, d_b, d_b, 3)    # output aliases b
+        assert np.array_equal(d_b.cpu().numpy(), want)
+
+
+@pytest.mark.parametrize("logn", [12, 16])
+def test_polymul_vs_oracle_pipeline(lib, oracle_mod, logn):
+    n = 1 << logn
+    rng = np.random.default_rng(7000 + logn)
+    fwd, inv = lib.negacyclic_tables(n, Q29, 3)
+    a = rng.integers(0, Q29, (2, n), dtype=np.int32)
+    b = rng.integers(0, Q29, (2, n), dtype=np.int32)
+    prod = oracle_mod.pointwise(oracle_mod.ntt_ct(a, fwd, Q29), oracle_mod.ntt_ct(b, fwd, Q29), Q29)
+    want = oracle_mod.scale(oracle_mod.ntt_gs(prod, inv, Q29), oracle_mod.powmod(n, Q29 - 2, Q29), Q29)
+    with lib.Plan(logn, Q29, fwd) as pf, lib.Plan(logn, Q29, inv) as pi:
+        d_c = torch.empty(2, n, dtype=torch.int32, device="cuda")
+        lib.polymul_negacyclic(pf, pi, dev(a), dev(b), d_c, 2)
+        assert np.array_equal(d_c.cpu().numpy(), want)
+
+
+def test_batch_independence(lib, oracle_mod):
+    """Polynomial k is unaffected by its neighbours; ragged batch sizes around the
+    kernel's grouping factors."""
+    n, p = 4096, Q29
+    rng = np.random.default_rng(8)
+    roots = lib.make_roots(n, p, 3)
+    a = rng.integers(0, p, (67, n), dtype=np.int32)
+    want = oracle_mod.ntt_gs(a, roots, p)
+    for batch in (1, 2, 7, 8, 9, 63, 67):
+        out, _ = run_gs(lib, a[:batch], roots, p)
+        assert np.array_equal(out, want[:batch]), batch
+    out, _ = run_gs(lib, a[:0].reshape(0, n), roots, p)   # empty batch
+    assert out.size == 0
+
+
+def test_host_buffer_entry_point(lib, oracle_mod):
+    """nttb200_gs_host: host in, host out (the reference's sync + launch + sync)."""
+    n, p = 4096, Q29
+    rng = np.random.default_rng(9)
+    roots = lib.make_roots(n, p, 3)
+    batch = 1500      # > one 16 MiB staging chunk (1024 polys), not a multiple
+    a = rng.integers(0, p, (batch, n), dtype=np.int32)
+    out = np.empty_like(a)
+    with lib.Plan(12, p, roots) as plan:
+        plan.gs_host(a, out, batch)
+    idx = [0, 1, 1023, 1024, 1025, batch - 1] + rng.integers(0, batch, 26).tolist()
+    assert np.array_equal(out[idx], oracle_mod.ntt_gs(a[idx], roots, p))
+    # the golden-signature wrapper
+    g = load_golden("default_n2048_p3329.npz")
+    assert np.array_equal(lib.ntt(g["a"], 2048, g["roots"], 3329, 10), g["out"])
+
+
+def test_full_size_properties(lib, oracle_mod):
+    """BASELINE config 2 shape (65,536 x N=4096): sampled rows against the oracle,
+    plus size-independent properties over the whole batch: linearity of the network
+    (NTT(a+b) = NTT(a)+NTT(b) mod q) and the CT o GS round trip = n * x."""
+    n, p, batch = 4096, Q29, 65536
+    roots = lib.make_roots(n, p, 3)
+    gen = torch.Generator(device="cuda").manual_seed(0x5EED0001)
+    a = torch.randint(0, p, (batch, n), dtype=torch.int32, device="cuda", generator=gen)
+    b = torch.randint(0, p, (batch, n), dtype=torch.int32, device="cuda", generator=gen)
+    fa, fb, fs = torch.empty_like(a), torch.empty_like(a), torch.empty_like(a)
+    with lib.Plan(12, p, roots) as plan:
+        plan.gs(a, fa, batch)
+        plan.gs(b, fb, batch)
+        s = (a + b) % p
+        plan.gs(s, fs, batch)
+        torch.cuda.synchronize()
+        assert plan.last_path != "none"
+    assert torch.equal(fs, (fa + fb) % p)
+    rng = np.random.default_rng(10)
+    idx = [0, 1, batch - 1] + rng.integers(0, batch, 253).tolist()
+    assert np.array_equal(fa[idx].cpu().numpy(), oracle_mod.ntt_gs(a[idx].cpu().numpy(), roots, p))
+    del fb, fs, s, b
+    fwd, inv = lib.negacyclic_tables(n, p, 3)
+    with lib.Plan(12, p, fwd) as pf, lib.Plan(12, p, inv) as pi:
+        pf.ct(a, fa, batch)
+        pi.gs(fa, fa, batch)
+        torch.cuda.synchronize()
+    assert torch.equal(fa, ((a.to(torch.int64) * n) % p).to(torch.int32))
