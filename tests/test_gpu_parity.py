@@ -253,3 +253,26 @@ def test_full_size_properties(lib, oracle_mod):
         pi.gs(fa, fa, batch)
         torch.cuda.synchronize()
     assert torch.equal(fa, ((a.to(torch.int64) * n) % p).to(torch.int32))
+
+
+def test_cpp_host_harness(lib):
+    """tests/host/ntt_test: the C++ successor of the reference's src/test.cpp main() --
+    default config, AIE device order, and a 29-bit batch -- prints PASS! and exits 0."""
+    import os
+    import subprocess
+    import sys
+    sys.path.insert(0, os.path.dirname(lib.lib_path()))
+    root = os.path.dirname(os.path.dirname(os.path.dirname(lib.lib_path())))
+    exe = os.path.join(root, "tests", "host", "ntt_test")
+    if not os.path.exists(exe):
+        import importlib.util
+        spec = importlib.util.spec_from_file_location(
+            "nttb200_build", os.path.join(root, "ntt-aie_b200", "build.py"))
+        mod = importlib.util.module_from_spec(spec)
+        spec.loader.exec_module(mod)
+        mod.build_host_harness()
+    for extra in ([], ["--aie-order"], ["--logn", "12", "--p", "469762049", "--batch", "33",
+                                        "--random", "--iters", "2"],
+                  ["--stage", "4"]):
+        res = subprocess.run([exe] + extra, capture_output=True, text=True, timeout=120)
+        assert res.returncode == 0 and "PASS!" in res.stdout, res.stdout + res.stderr
