@@ -20,7 +20,7 @@ LIB = os.path.join(LIBDIR, "libnttb200.so")
 NVCC = os.environ.get("NVCC") or shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
 NVCC_FLAGS = ["-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC,-fvisibility=hidden",
-              "--use_fast_math", "-Xptxas", "-v"] + ARCH
+              "--use_fast_math", "-Xptxas", "-v"] + ARCH + os.environ.get("NTTB200_NVCC_EXTRA", "").split()
 
 SOURCES = ["api.cu", "kernels_generic.cu", "kernels_fused.cu"]
 HEADERS = ["plan.h", "modarith.cuh", os.path.join(ROOT, "include", "nttb200.h")]

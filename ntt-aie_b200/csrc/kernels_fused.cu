@@ -36,7 +36,10 @@ namespace nttb200 {
 
 constexpr int kF_N = 4096;
 constexpr int kF_Team = 64;               // threads per polynomial
-constexpr int kF_Teams = 8;               // polynomials in flight per CTA
+#ifndef NTTB200_TEAMS
+#define NTTB200_TEAMS 8
+#endif
+constexpr int kF_Teams = NTTB200_TEAMS;   // polynomials in flight per CTA
 constexpr int kF_Threads = kF_Team * kF_Teams;
 constexpr int kF_TwSlots = 32;            // uint4 slots of round-1 twiddles per thread
 constexpr int kF_TwBytes = kF_TwSlots * kF_Team * 16;   // 32 KiB
