@@ -1,0 +1,128 @@
+"""One large transform split across G GPUs: local stages, ONE all-to-all, cross-GPU stages.
+
+The reference splits a single transform the same way one level down: each AIE tile
+runs the stages whose stride fits its contiguous slice (ntt_stage0_to_Nminus5,
+src/aie_core.cc:189-361), then the remaining log2(#tiles) stages pair whole slices
+between tiles with one broadcast twiddle each (ntt_1stage, src/aie_core.cc:161-187,
+scheduled in src/aie2.py:178-295).  Here the "tiles" are GPUs and the neighbour-memory
+exchange is an NCCL all-to-all over NVLink (torch.distributed.all_to_all_single) --
+the only collective on the path.
+
+    N = G * S, rank r owns the contiguous shard a[r*S, (r+1)*S).
+
+    step 1  stages 0 .. log2(S)-1 are local.  They are an ordinary length-S golden
+            transform with the DERIVED table
+                T_r[h + i] = table[h*(G + r) + i],   h = S/2, S/4, .., 1,  i < h
+            (global block index of local block i at a stage with h local blocks is
+            r*h + i, and the stage has G*h blocks in total).
+    step 2  all-to-all: rank r sends its k-th S/G slice to rank k.  Rank k then holds
+            rows[r][c] = a[r*S + k*S/G + c].
+    step 3  stages log2(S) .. log2(N)-1 pair rows r and r + 2^m; the twiddle is
+            table[(G >> (m+1)) + (r >> (m+1))] for every column.  On the local buffer
+            viewed as one length-S vector these are stages log2(S/G) .. log2(S)-1 of a
+            plan whose table starts with table[0..G).
+    step 4  (optional) a second all-to-all returns the result to the golden's natural
+            order; without it the output stays in the transposed order
+            out_k[r][c] = NTT(a)[r*S + k*S/G + c]   (documented like ans_order).
+
+Because the per-stage twiddles are taken from the caller's table by the golden's own
+index rule (src/test.cpp:45), the result is bit-exact against the golden ntt() for ANY
+table, not only DFT-valid ones.
+
+Nothing here computes on the host: the local work goes through an *engine* -- the
+CUDA plans of this package by default.  Tests inject a CPU engine to exercise the
+sharding logic over gloo.
+"""
+from __future__ import annotations
+
+from typing import Optional
+
+import numpy as np
+
+
+def shard_batch(batch: int, world: int, rank: int) -> tuple[int, int]:
+    """Contiguous [begin, end) of `batch` independent polynomials owned by `rank`
+    (batched configs shard with no communication)."""
+    return batch * rank // world, batch * (rank + 1) // world
+
+
+def local_table(table: np.ndarray, world: int, rank: int) -> np.ndarray:
+    """T_r of step 1 from the global table (length N, golden index rule)."""
+    n = table.shape[0]
+    s = n // world
+    out = np.zeros(s, dtype=np.int32)
+    h = s // 2
+    while h >= 1:
+        lo = h * (world + rank)
+        out[h:2 * h] = table[lo:lo + h]
+        h //= 2
+    return out
+
+
+def cross_table(table: np.ndarray, world: int, shard_len: int) -> np.ndarray:
+    """Table of step 3: a length-S table whose first G entries are table[0..G)."""
+    out = np.zeros(shard_len, dtype=np.int32)
+    out[:world] = table[:world]
+    return out
+
+
+class CudaEngine:
+    """Local stage executor backed by the CUDA plans (the product path)."""
+
+    def __init__(self, logs: int, q: int, t_local: np.ndarray, t_cross: np.ndarray, device: int):
+        from . import api
+        self.plan_local = api.Plan(logs, q, t_local, device=device)
+        self.plan_cross = api.Plan(logs, q, t_cross, device=device)
+
+    def local_full(self, buf) -> None:
+        self.plan_local.gs(buf, buf, 1)
+
+    def cross_stages(self, buf, stage_begin: int, stage_end: int) -> None:
+        self.plan_cross.gs_stage_range(buf, buf, 1, stage_begin, stage_end)
+
+    def close(self) -> None:
+        self.plan_local.close()
+        self.plan_cross.close()
+
+
+class FourStepNTT:
+    """Golden GS network of length N = 2^logn over `world` ranks (power of two)."""
+
+    def __init__(self, logn: int, q: int, table: np.ndarray, rank: int, world: int,
+                 device: Optional[int] = None, engine=None, group=None):
+        if world & (world - 1) or world < 1:
+            raise ValueError("world size must be a power of two")
+        self.logn, self.q, self.rank, self.world, self.group = logn, q, rank, world, group
+        self.n = 1 << logn
+        self.shard = self.n // world
+        self.logs = logn - (world.bit_length() - 1)
+        if self.shard < world:
+            raise ValueError("shard must hold at least one element per peer")
+        table = np.ascontiguousarray(table, dtype=np.int32)
+        if table.shape[0] != self.n:
+            raise ValueError("table must hold N words")
+        self.t_local = local_table(table, world, rank)
+        self.t_cross = cross_table(table, world, self.shard)
+        self.engine = engine if engine is not None else CudaEngine(
+            self.logs, q, self.t_local, self.t_cross, 0 if device is None else device)
+
+    def close(self) -> None:
+        if hasattr(self.engine, "close"):
+            self.engine.close()
+
+    def forward(self, shard, scratch, natural_order: bool = True):
+        """`shard`: this rank's S contiguous coefficients (torch int32 tensor on the
+        engine's device); `scratch`: same shape.  Returns the tensor holding the result
+        (one of the two buffers)."""
+        import torch.distributed as dist
+        eng, world = self.engine, self.world
+        eng.local_full(shard)                                   # step 1
+        if world == 1:
+            return shard
+        dist.all_to_all_single(scratch, shard, group=self.group)  # step 2 (the transpose)
+        logc = self.logs - (world.bit_length() - 1)
+        eng.cross_stages(scratch, logc, self.logs)               # step 3
+        if not natural_order:
+            return scratch
+        dist.all_to_all_single(shard, scratch, group=self.group)  # step 4
+        return shard

@@ -276,3 +276,23 @@ def test_cpp_host_harness(lib):
                   ["--stage", "4"]):
         res = subprocess.run([exe] + extra, capture_output=True, text=True, timeout=120)
         assert res.returncode == 0 and "PASS!" in res.stdout, res.stdout + res.stderr
+
+
+def test_fourstep_on_available_gpus(lib):
+    """tools/fourstep_run.py under torchrun on min(2, #GPUs) ranks: the whole N=2^18
+    vector bit-exact against the golden, for the reference table and an arbitrary one."""
+    import json
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.dirname(lib.lib_path())))
+    world = min(2, torch.cuda.device_count())
+    for extra in ([], ["--arbitrary-table"]):
+        cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1",
+               f"--nproc-per-node={world}", "--master-addr", "127.0.0.1", "--master-port", "29533",
+               os.path.join(root, "tools", "fourstep_run.py"), "--logn", "18", "--verify",
+               "--steps", "1", "--warmup", "1"] + extra
+        res = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
+        assert res.returncode == 0, res.stdout + res.stderr
+        line = json.loads([l for l in res.stdout.splitlines() if l.startswith("{")][-1])
+        assert line["bit_exact_vs_golden"] is True and line["n_gpus"] == world
