@@ -165,7 +165,10 @@ int nttb200_plan_create(nttb200_plan **out, int device, uint32_t logn, uint32_t 
     }
     if (!(flags & NTTB200_FORCE_GENERIC)) {
         int rc = fused_prepare(p);
+        if (rc == NTTB200_ERR_UNSUPPORTED) rc = multi_prepare(p);
         if (rc != NTTB200_OK && rc != NTTB200_ERR_UNSUPPORTED) {
+            fused_release(p);
+            multi_release(p);
             cudaFree(p->d_tw);
             delete p;
             return rc;
@@ -187,6 +190,7 @@ int nttb200_plan_destroy(nttb200_plan *p) {
         }
     }
     fused_release(p);
+    multi_release(p);
     if (p->d_tw) cudaFree(p->d_tw);
     delete p;
     return NTTB200_OK;
@@ -200,6 +204,10 @@ static int run_gs(nttb200_plan *p, const int32_t *d_in, int32_t *d_out, size_t b
     if (full && !(p->flags & NTTB200_FORCE_GENERIC)) {
         int rc = launch_fused_gs(p, d_in, d_out, batch, permute, st);
         if (rc != NTTB200_ERR_UNSUPPORTED) return rc;
+        if (!permute) {
+            rc = launch_multi_gs(p, d_in, d_out, batch, st);
+            if (rc != NTTB200_ERR_UNSUPPORTED) return rc;
+        }
     }
     p->last_path = "generic_stage_pass";
     int se = full ? (int) p->logn : stage_limit + 1;
@@ -239,9 +247,27 @@ int nttb200_gs_stage_range(nttb200_plan *p, const int32_t *d_in, int32_t *d_out,
         }
         return NTTB200_OK;
     }
+    cudaStream_t st = (cudaStream_t) stream;
+    // stages that pair coefficients >= 4 apart run as register-radix column passes
+    if (stage_begin >= 2 && !(p->flags & NTTB200_FORCE_GENERIC) && !((uintptr_t) d_in & 15u) &&
+        !((uintptr_t) d_out & 15u)) {
+        int rest = stage_end - stage_begin;
+        int passes = (rest + 5) / 6;
+        int s0 = stage_begin;
+        const int32_t *src = d_in;
+        int rc = NTTB200_OK;
+        for (int k = 0; k < passes && rc == NTTB200_OK; k++) {
+            int take = (rest + (passes - k) - 1) / (passes - k);
+            rc = launch_column_pass(p, src, d_out, batch, s0, take, st);
+            src = d_out;
+            s0 += take;
+            rest -= take;
+        }
+        p->last_path = "column_passes";
+        return rc;
+    }
     p->last_path = "generic_stage_pass";
-    return launch_generic(p, d_in, d_out, batch, stage_begin, stage_end, false, false,
-                          (cudaStream_t) stream);
+    return launch_generic(p, d_in, d_out, batch, stage_begin, stage_end, false, false, st);
 }
 
 static int host_prepare(nttb200_plan *p) {

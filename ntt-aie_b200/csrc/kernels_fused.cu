@@ -29,13 +29,12 @@
 
 #include <vector>
 
-#include "modarith.cuh"
+#include "fused_common.cuh"
 #include "plan.h"
 
 namespace nttb200 {
 
 constexpr int kF_N = 4096;
-constexpr int kF_Team = 64;               // threads per polynomial
 #ifndef NTTB200_TEAMS
 #define NTTB200_TEAMS 8
 #endif
@@ -43,80 +42,7 @@ constexpr int kF_Teams = NTTB200_TEAMS;   // polynomials in flight per CTA
 constexpr int kF_Threads = kF_Team * kF_Teams;
 constexpr int kF_TwSlots = 32;            // uint4 slots of round-1 twiddles per thread
 constexpr int kF_TwBytes = kF_TwSlots * kF_Team * 16;   // 32 KiB
-constexpr int kF_PolyBytes = kF_N * 4;                  // 16 KiB
 constexpr int kF_SmemBytes = kF_TwBytes + kF_Teams * kF_PolyBytes + 64 + 1024;
-
-// ---------------------------------------------------------------- PTX helpers
-__device__ __forceinline__ uint32_t smem_u32(const void *p) {
-    return (uint32_t) __cvta_generic_to_shared(p);
-}
-__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
-}
-__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes)
-                 : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
-    asm volatile(
-        "{\n"
-        ".reg .pred p;\n"
-        "WAIT_LOOP:\n"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
-        "@p bra WAIT_DONE;\n"
-        "bra WAIT_LOOP;\n"
-        "WAIT_DONE:\n"
-        "}\n" ::"r"(bar),
-        "r"(parity)
-        : "memory");
-}
-__device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap *map, uint32_t bar,
-                                            int c0, int c1, int c2) {
-    asm volatile(
-        "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes"
-        " [%0], [%1, {%3, %4, %5}], [%2];" ::"r"(dst),
-        "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2)
-        : "memory");
-}
-__device__ __forceinline__ void fence_proxy_async() {
-    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-}
-__device__ __forceinline__ void team_sync(int team) {
-    asm volatile("bar.sync %0, %1;" ::"r"(team + 1), "n"(kF_Team) : "memory");
-}
-__device__ __forceinline__ uint4 lds128(uint32_t addr) {
-    uint4 v;
-    asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];"
-                 : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w)
-                 : "r"(addr));
-    return v;
-}
-__device__ __forceinline__ void sts128(uint32_t addr, uint32_t a, uint32_t b, uint32_t c,
-                                       uint32_t d) {
-    asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c),
-                 "r"(d)
-                 : "memory");
-}
-__device__ __forceinline__ uint32_t lds32(uint32_t addr) {
-    uint32_t v;
-    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr));
-    return v;
-}
-
-// ------------------------------------------------------------------ butterfly
-// Lazy GS butterfly on values in [0, 2q).  `zero` is an opaque runtime 0 that keeps
-// the add a 3-input IADD3 on the ALU pipe (ptxas would otherwise turn half of the
-// plain adds into IMAD.IADD on the FMA pipe, which the three multiplies saturate).
-template <bool REDUCE>
-__device__ __forceinline__ void gs_bfly(uint32_t &x, uint32_t &y, uint32_t w, uint32_t wp,
-                                        uint32_t q, uint32_t two_q, uint32_t zero) {
-    uint32_t s = x + y + zero;
-    uint32_t d = x - y + two_q;
-    if (REDUCE) s = min(s - two_q, s);
-    uint32_t h = __umulhi(d, wp);
-    x = s;
-    y = d * w - h * q;
-}
 
 // last stage: canonical outputs in [0, q)
 __device__ __forceinline__ void gs_bfly_final(uint32_t &x, uint32_t &y, uint32_t w, uint32_t wp,
@@ -332,6 +258,13 @@ static int make_half_map(CUtensorMap *map, const int32_t *base, size_t batch) {
                      CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
                      CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     return r == CUDA_SUCCESS ? NTTB200_OK : NTTB200_ERR_CUDA;
+}
+
+// both half-tile maps of a buffer of `tiles` contiguous 4096-word tiles
+int tile_maps(CUtensorMap *lo, CUtensorMap *hi, const int32_t *base, size_t tiles) {
+    int rc = make_half_map(lo, base, tiles);
+    if (rc == NTTB200_OK) rc = make_half_map(hi, base + 32, tiles);
+    return rc;
 }
 
 int fused_prepare(nttb200_plan *p) {

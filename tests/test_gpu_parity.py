@@ -296,3 +296,42 @@ def test_fourstep_on_available_gpus(lib):
         assert res.returncode == 0, res.stdout + res.stderr
         line = json.loads([l for l in res.stdout.splitlines() if l.startswith("{")][-1])
         assert line["bit_exact_vs_golden"] is True and line["n_gpus"] == world
+
+
+@pytest.mark.parametrize("logn", [6, 13, 17, 20])
+def test_stage_range_vs_restatement(lib, oracle_mod, logn):
+    """nttb200_gs_stage_range against the vectorised restatement of src/test.cpp:36-59
+    (itself pinned to the oracle in tests/test_multigpu_cpu.py), incl. in place and the
+    column-pass path (stage_begin >= 2)."""
+    from test_multigpu_cpu import gs_stage_range_numpy
+    n = 1 << logn
+    rng = np.random.default_rng(9000 + logn)
+    table = rng.integers(0, Q29, n, dtype=np.int32)
+    a = rng.integers(0, Q29, (2, n), dtype=np.int32)
+    ranges = [(0, logn), (0, 1), (2, logn), (logn - 3, logn), (3, 3), (logn // 2, logn // 2 + 1),
+              (1, logn - 1), (logn - 1, logn)]
+    with lib.Plan(logn, Q29, table) as plan:
+        for sb, se in ranges:
+            d = dev(a)
+            out = torch.empty_like(d)
+            plan.gs_stage_range(d, out, 2, sb, se)
+            want = np.stack([gs_stage_range_numpy(x, table, Q29, sb, se) for x in a])
+            assert np.array_equal(out.cpu().numpy(), want), (logn, sb, se, plan.last_path)
+            plan.gs_stage_range(d, d, 2, sb, se)
+            assert np.array_equal(d.cpu().numpy(), want), (logn, sb, se, "in place")
+
+
+@pytest.mark.parametrize("logn", [13, 15, 16, 18, 21])
+def test_large_n_multi_pass_path(lib, oracle_mod, logn):
+    """logn >= 13 takes the tile pass + column passes; batch sizes around the CTA
+    range partition, arbitrary tables."""
+    n = 1 << logn
+    rng = np.random.default_rng(9500 + logn)
+    table = rng.integers(0, Q29, n, dtype=np.int32)
+    for batch in ((1, 3, 40) if logn <= 16 else (1, 2)):
+        a = rng.integers(0, Q29, (batch, n), dtype=np.int32)
+        out, path = run_gs(lib, a, table, Q29)
+        assert "tile" in path, path
+        assert np.array_equal(out, oracle_mod.ntt_gs(a, table, Q29)), (logn, batch)
+        out, _ = run_gs(lib, a, table, Q29, inplace=True)
+        assert np.array_equal(out, oracle_mod.ntt_gs(a, table, Q29)), (logn, batch, "in place")

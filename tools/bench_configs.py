@@ -1,0 +1,173 @@
+#!/usr/bin/env python
+"""Secondary measurements for the BASELINE.json configs bench.py does not headline.
+
+    python tools/bench_configs.py [--configs 1,3,4] [--reps 20]
+
+cfg1  single forward NTT at the reference default (N=2048, p=3329, a[i]=i): parity
+      against the golden + latency per host-buffer call (the reference reports host
+      wall time per launch the same way, src/test.cpp:157-175; trimmed mean dropping
+      min and max as profile/plot_exectime.py:27-29 does).
+cfg3  negacyclic polynomial multiply sweep N = 2^12 .. 2^16, batch = 2^26/N products:
+      products/s and algorithmic GB/s (12 N bytes per product) vs the measured HBM peak.
+cfg4  batched NTT N = 2^16, 4096 polynomials (2^28 coefficients) on this GPU's shard:
+      polys/s and algorithmic GB/s (8 N bytes per polynomial).
+ntt   forward GS NTT sweep N = 2^10 .. 2^16 at 2^26 coefficients (context for cfg3/4).
+
+One JSON line per measurement on stdout.  Device-timed with CUDA events on the
+launching stream, 3 warm-ups, inputs larger than L2.  Every timed configuration is
+parity-checked on sampled polynomials against the oracle (test infrastructure).
+"""
+import argparse
+import json
+import os
+import statistics
+import sys
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import ntt_aie_b200 as nt  # noqa: E402
+import oracle  # noqa: E402
+
+Q = 469762049
+
+
+def peak():
+    try:
+        return float(json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"])
+    except Exception:
+        return 6650.0
+
+
+def trimmed(ms):
+    ms = sorted(ms)
+    return statistics.mean(ms[1:-1]) if len(ms) > 2 else statistics.mean(ms)
+
+
+def time_launches(fn, reps, warmup=3):
+    for _ in range(warmup):
+        fn()
+    torch.cuda.synchronize()
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(reps + 1)]
+    ev[0].record()
+    for k in range(reps):
+        fn()
+        ev[k + 1].record()
+    torch.cuda.synchronize()
+    return [ev[k].elapsed_time(ev[k + 1]) for k in range(reps)]
+
+
+def cfg1(reps):
+    n, p, g = 2048, 3329, 3
+    roots = nt.make_roots(n, p, g)
+    a = np.arange(n, dtype=np.int32)
+    want = oracle.ntt_gs(a, oracle.make_roots(n, p, g), p, 10)
+    out = np.empty_like(a)
+    import time
+    with nt.Plan(11, p, roots) as plan:
+        plan.gs_host(a, out, 1, 10)
+        ok = bool(np.array_equal(out, want))
+        us = []
+        for _ in range(max(reps, 10)):
+            t0 = time.perf_counter()
+            plan.gs_host(a, out, 1, 10)
+            us.append((time.perf_counter() - t0) * 1e6)
+        d_in = torch.from_numpy(a).cuda()
+        d_out = torch.empty_like(d_in)
+        ms = time_launches(lambda: plan.gs(d_in, d_out, 1, 10), reps)
+        path = plan.last_path
+    us.sort()
+    print(json.dumps({"config": "cfg1 single forward NTT N=2048 p=3329 a[i]=i", "bit_exact": ok,
+                      "host_call_us_trimmed_mean": statistics.mean(us[1:-1]),
+                      "device_kernel_us_trimmed_mean": trimmed(ms) * 1e3, "kernel_path": path,
+                      "reference_npu_wall_us": 279, "reference_npu_kernel_us": 14.375}), flush=True)
+
+
+def ntt_sweep(reps, logns):
+    for logn in logns:
+        n = 1 << logn
+        batch = (1 << 26) // n
+        roots = nt.make_roots(n, Q, 3)
+        gen = torch.Generator(device="cuda").manual_seed(logn)
+        d_in = torch.randint(0, Q, (batch, n), dtype=torch.int32, device="cuda", generator=gen)
+        d_out = torch.empty_like(d_in)
+        with nt.Plan(logn, Q, roots) as plan:
+            ms = time_launches(lambda: plan.gs(d_in, d_out, batch), reps)
+            path = plan.last_path
+        idx = [0, batch - 1, batch // 2]
+        ok = bool(np.array_equal(d_out[idx].cpu().numpy(),
+                                 oracle.ntt_gs(d_in[idx].cpu().numpy(), roots, Q)))
+        t = trimmed(ms) * 1e-3
+        gbs = batch * n * 8 / t / 1e9
+        print(json.dumps({"config": f"ntt forward GS N=2^{logn} batch={batch}", "logn": logn,
+                          "polys_per_s": batch / t, "butterflies_per_s": batch * (n // 2) * logn / t,
+                          "algorithmic_GBps": gbs, "frac_of_measured_hbm": gbs / peak(),
+                          "ms": t * 1e3, "kernel_path": path, "bit_exact_sampled": ok}), flush=True)
+
+
+def cfg3(reps):
+    for logn in range(12, 17):
+        n = 1 << logn
+        batch = (1 << 26) // n
+        fwd, inv = nt.negacyclic_tables(n, Q, 3)
+        gen = torch.Generator(device="cuda").manual_seed(100 + logn)
+        d_a = torch.randint(0, Q, (batch, n), dtype=torch.int32, device="cuda", generator=gen)
+        d_b = torch.randint(0, Q, (batch, n), dtype=torch.int32, device="cuda", generator=gen)
+        d_c = torch.empty_like(d_a)
+        with nt.Plan(logn, Q, fwd) as pf, nt.Plan(logn, Q, inv) as pi:
+            ms = time_launches(lambda: nt.polymul_negacyclic(pf, pi, d_a, d_b, d_c, batch), reps)
+        idx = [0, batch - 1]
+        a, b = d_a[idx].cpu().numpy(), d_b[idx].cpu().numpy()
+        prod = oracle.pointwise(oracle.ntt_ct(a, fwd, Q), oracle.ntt_ct(b, fwd, Q), Q)
+        want = oracle.scale(oracle.ntt_gs(prod, inv, Q), oracle.powmod(n, Q - 2, Q), Q)
+        ok = bool(np.array_equal(d_c[idx].cpu().numpy(), want))
+        t = trimmed(ms) * 1e-3
+        gbs = batch * n * 12 / t / 1e9
+        print(json.dumps({"config": f"cfg3 negacyclic polymul N=2^{logn} batch={batch}",
+                          "logn": logn, "products_per_s": batch / t, "algorithmic_GBps": gbs,
+                          "frac_of_measured_hbm": gbs / peak(), "ms": t * 1e3,
+                          "butterflies_per_s": 3 * batch * (n // 2) * logn / t,
+                          "bit_exact_sampled": ok}), flush=True)
+
+
+def cfg4(reps):
+    logn, batch = 16, 4096
+    n = 1 << logn
+    roots = nt.make_roots(n, Q, 3)
+    gen = torch.Generator(device="cuda").manual_seed(16)
+    d_in = torch.randint(0, Q, (batch, n), dtype=torch.int32, device="cuda", generator=gen)
+    d_out = torch.empty_like(d_in)
+    with nt.Plan(logn, Q, roots) as plan:
+        ms = time_launches(lambda: plan.gs(d_in, d_out, batch), reps)
+        path = plan.last_path
+    idx = [0, batch - 1, 1234]
+    ok = bool(np.array_equal(d_out[idx].cpu().numpy(),
+                             oracle.ntt_gs(d_in[idx].cpu().numpy(), roots, Q)))
+    t = trimmed(ms) * 1e-3
+    gbs = batch * n * 8 / t / 1e9
+    print(json.dumps({"config": "cfg4 batched NTT N=2^16 x 4096 polys (one GPU's full set)",
+                      "polys_per_s": batch / t, "butterflies_per_s": batch * (n // 2) * logn / t,
+                      "algorithmic_GBps": gbs, "frac_of_measured_hbm": gbs / peak(),
+                      "ms": t * 1e3, "kernel_path": path, "bit_exact_sampled": ok}), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--configs", default="1,ntt,3,4")
+    ap.add_argument("--reps", type=int, default=20)
+    args = ap.parse_args()
+    todo = args.configs.split(",")
+    if "1" in todo:
+        cfg1(args.reps)
+    if "ntt" in todo:
+        ntt_sweep(args.reps, range(10, 17))
+    if "3" in todo:
+        cfg3(args.reps)
+    if "4" in todo:
+        cfg4(args.reps)
+
+
+if __name__ == "__main__":
+    main()
