@@ -165,7 +165,10 @@ int nttb200_plan_create(nttb200_plan **out, int device, uint32_t logn, uint32_t 
     }
     if (!(flags & NTTB200_FORCE_GENERIC)) {
         int rc = fused_prepare(p);
-        if (rc == NTTB200_ERR_UNSUPPORTED) rc = multi_prepare(p);
+        if (rc == NTTB200_OK || rc == NTTB200_ERR_UNSUPPORTED) {
+            int rc2 = multi_prepare(p);
+            if (rc2 != NTTB200_ERR_UNSUPPORTED) rc = rc2;
+        }
         if (rc != NTTB200_OK && rc != NTTB200_ERR_UNSUPPORTED) {
             fused_release(p);
             multi_release(p);
@@ -228,6 +231,10 @@ int nttb200_ct_batch(nttb200_plan *p, const int32_t *d_in, int32_t *d_out, size_
     // CT stage idx (0 = stride N/2) acts on index bit logn-1-idx
     const bool full = full_depth(p, stage_limit);
     int sb = full ? 0 : (int) p->logn - 1 - stage_limit;
+    if (full && !(p->flags & NTTB200_FORCE_GENERIC)) {
+        int rc = launch_multi_ct(p, d_in, d_out, batch, (cudaStream_t) stream);
+        if (rc != NTTB200_ERR_UNSUPPORTED) return rc;
+    }
     p->last_path = "generic_stage_pass";
     return launch_generic(p, d_in, d_out, batch, sb, (int) p->logn, /*ct=*/true, false,
                           (cudaStream_t) stream);
@@ -348,6 +355,22 @@ int nttb200_polymul_negacyclic(nttb200_plan *fwd, nttb200_plan *inv, const int32
     const size_t words = batch * fwd->n;
     // scratch for NTT(b) (and NTT(a) when the output aliases b)
     int32_t *tmp = nullptr;
+    const bool fast = !((fwd->flags | inv->flags) & NTTB200_FORCE_GENERIC) && fwd->d_tw_tile &&
+                      inv->d_tw_tile;
+    if (fast) {
+        // NTT(a), NTT(b) into scratch; pointwise product, inverse transform and the
+        // N^-1 scaling in one pass over them
+        NTTB200_CUDA(cudaMallocAsync(&tmp, sizeof(int32_t) * words * 2, st));
+        int rc = launch_multi_ct(fwd, d_a, tmp, batch, st);
+        if (rc == NTTB200_OK) rc = launch_multi_ct(fwd, d_b, tmp + words, batch, st);
+        if (rc == NTTB200_OK) rc = launch_multi_gs_dual(inv, tmp, tmp + words, d_c, batch, st);
+        cudaError_t e = cudaFreeAsync(tmp, st);
+        if (rc != NTTB200_ERR_UNSUPPORTED) {
+            if (rc == NTTB200_OK && e != cudaSuccess) rc = cuda_fail(e, "cudaFreeAsync");
+            return rc;
+        }
+        tmp = nullptr;  // fall through to the generic pipeline (nothing was written to d_c)
+    }
     NTTB200_CUDA(cudaMallocAsync(&tmp, sizeof(int32_t) * words, st));
     int rc = launch_generic(fwd, d_b, tmp, batch, 0, (int) fwd->logn, true, false, st);
     if (rc == NTTB200_OK) rc = launch_generic(fwd, d_a, d_c, batch, 0, (int) fwd->logn, true, false, st);

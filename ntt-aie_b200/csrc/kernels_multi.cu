@@ -59,6 +59,56 @@ __device__ __forceinline__ void gs_stage_g(uint32_t (&v)[64], const uint4 *tw, u
     }
 }
 
+
+// Lazy Harvey Cooley-Tukey butterfly on values in [0, 4q): x is brought to [0, 2q),
+// v = y*w in [0, 2q) by Shoup; outputs x+v and x-v+2q, both in [0, 4q).  4q < 2^32.
+template <bool REDUCE_X>
+__device__ __forceinline__ void ct_bfly(uint32_t &x, uint32_t &y, uint32_t w, uint32_t wp,
+                                        uint32_t q, uint32_t two_q, uint32_t zero) {
+    uint32_t xr = REDUCE_X ? min(x - two_q, x) : x;
+    uint32_t h = __umulhi(y, wp);
+    uint32_t v = y * w - h * q;
+    x = xr + v + zero;
+    y = xr - v + two_q;
+}
+
+// CT stage on the thread's 64 registers (pairs i, i + 2^S), same twiddle slots as GS
+template <int S, bool REDUCE_X>
+__device__ __forceinline__ void ct_stage_g(uint32_t (&v)[64], const uint4 *tw, uint32_t q,
+                                           uint32_t two_q, uint32_t zero) {
+    constexpr int kBlocks = 32 >> S;
+    constexpr int kSlot0 = 32 - (kBlocks >= 2 ? kBlocks : 1);
+    constexpr int kStride = 1 << S;
+#pragma unroll
+    for (int b = 0; b < kBlocks; b += 2) {
+        uint4 t = ldg128(tw + (kSlot0 + b / 2) * kM_TwRow);
+#pragma unroll
+        for (int e = 0; e < kStride; e++) {
+            int i0 = b * 2 * kStride + e;
+            ct_bfly<REDUCE_X>(v[i0], v[i0 + kStride], t.x, t.y, q, two_q, zero);
+        }
+        if (kBlocks >= 2) {
+#pragma unroll
+            for (int e = 0; e < kStride; e++) {
+                int i0 = (b + 1) * 2 * kStride + e;
+                ct_bfly<REDUCE_X>(v[i0], v[i0 + kStride], t.z, t.w, q, two_q, zero);
+            }
+        }
+    }
+}
+
+__device__ __forceinline__ void tma_store_3d(const CUtensorMap *map, uint32_t src, int c0, int c1,
+                                             int c2) {
+    asm volatile(
+        "cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];" ::"l"(map),
+        "r"(src), "r"(c0), "r"(c1), "r"(c2)
+        : "memory");
+}
+__device__ __forceinline__ void tma_store_commit_and_wait_read() {
+    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+    asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+}
+
 struct TileParams {
     uint32_t *out;
     const uint4 *tw_tile;  // [chunks][32][65]
@@ -66,11 +116,22 @@ struct TileParams {
     uint32_t chunks;       // tiles per polynomial
     uint32_t q;
     uint32_t zero;
+    uint32_t qinv;         // q^-1 mod 2^32 (DUAL: Montgomery product of the two inputs)
+    uint32_t scale;        // DUAL: every output is multiplied by this constant (Shoup pair)
+    uint32_t scale_shoup;
 };
 
+// DUAL = false: plain golden stages 0..11 of every tile.
+// DUAL = true : the tile's input is the pointwise product of two buffers (second pair
+//   of tensor maps), taken as a Montgomery product a*b*2^-32, and every output is
+//   multiplied by `scale` (= N^-1 * 2^32 mod q for the inverse transform of a
+//   negacyclic product).  The network is linear, so scaling here instead of after the
+//   last column pass gives the same residues.
+template <bool DUAL>
 __global__ void __launch_bounds__(kM_Threads, 1)
 tile_gs_kernel(const __grid_constant__ CUtensorMap map_lo, const __grid_constant__ CUtensorMap map_hi,
-               const TileParams prm) {
+               const __grid_constant__ CUtensorMap map_b_lo,
+               const __grid_constant__ CUtensorMap map_b_hi, const TileParams prm) {
     extern __shared__ uint8_t smem_raw[];
     const uint32_t data_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
     const uint32_t bar_base = data_base + kM_Teams * kF_PolyBytes;
@@ -127,8 +188,30 @@ tile_gs_kernel(const __grid_constant__ CUtensorMap map_lo, const __grid_constant
             v[4 * c + 2] = t.z;
             v[4 * c + 3] = t.w;
         }
+        if (DUAL) {
+            // second operand through the same buffer, then v = a*b*2^-32 mod q in (0, 2q)
+            team_sync(team);
+            if (j == 0) {
+                mbar_expect_tx(bar, kF_PolyBytes);
+                tma_load_3d(buf, &map_b_lo, bar, 0, 0, (int) tile_cur);
+                tma_load_3d(buf + kF_PolyBytes / 2, &map_b_hi, bar, 0, 0, (int) tile_cur);
+            }
+            mbar_wait(bar, parity);
+            parity ^= 1;
+#pragma unroll
+            for (int c = 0; c < 16; c++) {
+                uint4 t = lds128(r1_row + (c >> 3) * (kF_PolyBytes / 2) + (((c & 7) << 4) ^ r1_xor));
+                const uint32_t bb[4] = {t.x, t.y, t.z, t.w};
+#pragma unroll
+                for (int e = 0; e < 4; e++) {
+                    uint64_t prod = (uint64_t) v[4 * c + e] * bb[e];
+                    uint32_t m = (uint32_t) prod * prm.qinv;
+                    v[4 * c + e] = (uint32_t) (prod >> 32) - __umulhi(m, q) + q;
+                }
+            }
+        }
         const uint4 *tw1 = tw + j;
-        gs_stage_g<0, false>(v, tw1, q, two_q, zero);
+        gs_stage_g<0, DUAL>(v, tw1, q, two_q, zero);
         gs_stage_g<1, true>(v, tw1, q, two_q, zero);
         gs_stage_g<2, true>(v, tw1, q, two_q, zero);
         gs_stage_g<3, true>(v, tw1, q, two_q, zero);
@@ -167,8 +250,131 @@ tile_gs_kernel(const __grid_constant__ CUtensorMap map_lo, const __grid_constant
 
         uint32_t *dst = prm.out + (size_t) tile_store * 4096 + j;
 #pragma unroll
-        for (int i = 0; i < 64; i++) dst[i * 64] = min(v[i] - q, v[i]);
+        for (int i = 0; i < 64; i++) {
+            uint32_t r = DUAL ? shoup_mul_lazy(v[i], prm.scale, prm.scale_shoup, q) : v[i];
+            dst[i * 64] = min(r - q, r);
+        }
     }
+}
+
+// Forward partner: CT stages 11..0 of every tile (stride 2048 -> 1).  Columns first
+// (uniform twiddles), exchange, rows (thread-private twiddles); the rows go back to the
+// team's buffer and leave through a TMA store.
+__global__ void __launch_bounds__(kM_Threads, 1)
+tile_ct_kernel(const __grid_constant__ CUtensorMap map_lo, const __grid_constant__ CUtensorMap map_hi,
+               const __grid_constant__ CUtensorMap out_lo, const __grid_constant__ CUtensorMap out_hi,
+               const TileParams prm) {
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t data_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    const uint32_t bar_base = data_base + kM_Teams * kF_PolyBytes;
+    const int tid = threadIdx.x;
+    const int team = tid >> 6;
+    const int j = tid & 63;
+    const uint32_t q = prm.q, two_q = 2u * prm.q, zero = prm.zero;
+
+    if (tid < kM_Teams) mbar_init(bar_base + tid * 8, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    __syncthreads();
+
+    const uint64_t total = (uint64_t) prm.batch * prm.chunks;
+    const uint64_t u_begin = total * blockIdx.x / gridDim.x;
+    const uint64_t u_end = total * (blockIdx.x + 1) / gridDim.x;
+    const uint32_t buf = data_base + team * kF_PolyBytes;
+    const uint32_t bar = bar_base + team * 8;
+    uint32_t parity = 0;
+    uint64_t u = u_begin + team;
+    auto tile_of = [&](uint64_t uu, uint32_t &c) -> uint32_t {
+        c = (uint32_t) (uu / prm.batch);
+        uint32_t poly = (uint32_t) (uu - (uint64_t) c * prm.batch);
+        return poly * prm.chunks + c;
+    };
+    uint32_t c_cur = 0, tile_cur = 0;
+    if (u < u_end) {
+        tile_cur = tile_of(u, c_cur);
+        if (j == 0) {
+            mbar_expect_tx(bar, kF_PolyBytes);
+            tma_load_3d(buf, &map_lo, bar, 0, 0, (int) tile_cur);
+            tma_load_3d(buf + kF_PolyBytes / 2, &map_hi, bar, 0, 0, (int) tile_cur);
+        }
+    }
+    const uint32_t r1_row = buf + j * 128;
+    const uint32_t r1_xor = (j & 7) << 4;
+    const uint32_t r2_col = buf + (j >> 5) * (kF_PolyBytes / 2) + (j & 3) * 4;
+    const uint32_t r2_chunk = ((j & 31) >> 2) << 4;
+
+    for (; u < u_end; u += kM_Teams) {
+        uint32_t v[64];
+        const uint4 *tw = prm.tw_tile + (size_t) c_cur * kM_TwTile;
+        mbar_wait(bar, parity);
+        parity ^= 1;
+        // ---- columns: register i = a[j + 64 i]; stages 11..6
+#pragma unroll
+        for (int i = 0; i < 64; i++) {
+            v[i] = lds32(r2_col + i * 128 + (r2_chunk ^ ((i & 7) << 4)));
+        }
+        const uint4 *tw2 = tw + 64;
+        ct_stage_g<5, false>(v, tw2, q, two_q, zero);
+        ct_stage_g<4, true>(v, tw2, q, two_q, zero);
+        ct_stage_g<3, true>(v, tw2, q, two_q, zero);
+        ct_stage_g<2, true>(v, tw2, q, two_q, zero);
+        ct_stage_g<1, true>(v, tw2, q, two_q, zero);
+        ct_stage_g<0, true>(v, tw2, q, two_q, zero);
+        // ---- exchange: column write, row read (thread j owns a[64j .. 64j+63])
+#pragma unroll
+        for (int i = 0; i < 64; i++) {
+            asm volatile("st.shared.u32 [%0], %1;" ::"r"(r2_col + i * 128 + (r2_chunk ^ ((i & 7) << 4))),
+                         "r"(v[i])
+                         : "memory");
+        }
+        team_sync(team);
+#pragma unroll
+        for (int c = 0; c < 16; c++) {
+            uint4 t = lds128(r1_row + (c >> 3) * (kF_PolyBytes / 2) + (((c & 7) << 4) ^ r1_xor));
+            v[4 * c + 0] = t.x;
+            v[4 * c + 1] = t.y;
+            v[4 * c + 2] = t.z;
+            v[4 * c + 3] = t.w;
+        }
+        // ---- rows: stages 5..0
+        const uint4 *tw1 = tw + j;
+        ct_stage_g<5, true>(v, tw1, q, two_q, zero);
+        ct_stage_g<4, true>(v, tw1, q, two_q, zero);
+        ct_stage_g<3, true>(v, tw1, q, two_q, zero);
+        ct_stage_g<2, true>(v, tw1, q, two_q, zero);
+        ct_stage_g<1, true>(v, tw1, q, two_q, zero);
+        ct_stage_g<0, true>(v, tw1, q, two_q, zero);
+        // ---- canonical rows back to the buffer, TMA store, then the next load
+#pragma unroll
+        for (int c = 0; c < 16; c++) {
+            uint32_t o[4];
+#pragma unroll
+            for (int e = 0; e < 4; e++) {
+                uint32_t r = v[4 * c + e];
+                r = min(r - two_q, r);
+                o[e] = min(r - q, r);
+            }
+            sts128(r1_row + (c >> 3) * (kF_PolyBytes / 2) + (((c & 7) << 4) ^ r1_xor), o[0], o[1],
+                   o[2], o[3]);
+        }
+        fence_proxy_async();
+        team_sync(team);
+        const uint64_t next = u + kM_Teams;
+        uint32_t tile_next = 0;
+        if (next < u_end) tile_next = tile_of(next, c_cur);
+        if (j == 0) {
+            tma_store_3d(&out_lo, buf, 0, 0, (int) tile_cur);
+            tma_store_3d(&out_hi, buf + kF_PolyBytes / 2, 0, 0, (int) tile_cur);
+            tma_store_commit_and_wait_read();
+            if (next < u_end) {
+                mbar_expect_tx(bar, kF_PolyBytes);
+                tma_load_3d(buf, &map_lo, bar, 0, 0, (int) tile_next);
+                tma_load_3d(buf + kF_PolyBytes / 2, &map_hi, bar, 0, 0, (int) tile_next);
+            }
+        }
+        tile_cur = tile_next;
+    }
+    // the last store must have left shared memory before the CTA exits
+    if (j == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
 }
 
 // ------------------------------------------------------------------ column pass
@@ -185,10 +391,10 @@ template <> struct VecT<1> { using type = uint32_t; };
 template <> struct VecT<2> { using type = uint2; };
 template <> struct VecT<4> { using type = uint4; };
 
-template <int K, int VC>
+template <int K, int VC, bool CT>
 __global__ void __launch_bounds__(256)
-column_gs_kernel(const uint32_t *__restrict__ in, uint32_t *__restrict__ out,
-                 const uint2 *__restrict__ tw, const ColParams p) {
+column_kernel(const uint32_t *__restrict__ in, uint32_t *__restrict__ out,
+              const uint2 *__restrict__ tw, const ColParams p) {
     constexpr int R = 1 << K;
     using V = typename VecT<VC>::type;
     const uint32_t q = p.q, two_q = 2u * p.q, zero = p.zero;
@@ -211,7 +417,8 @@ column_gs_kernel(const uint32_t *__restrict__ in, uint32_t *__restrict__ out,
             for (int c = 0; c < VC; c++) v[r][c] = xs[c];
         }
 #pragma unroll
-        for (int m = 0; m < K; m++) {
+        for (int mm = 0; mm < K; mm++) {
+            const int m = CT ? K - 1 - mm : mm;  // CT: largest stride first
             const uint32_t s = p.s0 + m;
             const uint2 *tws = tw + (n >> (s + 1)) + ((size_t) high << (K - m - 1));
 #pragma unroll
@@ -222,7 +429,13 @@ column_gs_kernel(const uint32_t *__restrict__ in, uint32_t *__restrict__ out,
                     const int r0 = (b << (m + 1)) + e;
 #pragma unroll
                     for (int c = 0; c < VC; c++) {
-                        if (m == 0) {
+                        if (CT) {
+                            if (mm == 0) {
+                                ct_bfly<false>(v[r0][c], v[r0 + (1 << m)][c], w.x, w.y, q, two_q, zero);
+                            } else {
+                                ct_bfly<true>(v[r0][c], v[r0 + (1 << m)][c], w.x, w.y, q, two_q, zero);
+                            }
+                        } else if (mm == 0) {
                             gs_bfly<false>(v[r0][c], v[r0 + (1 << m)][c], w.x, w.y, q, two_q, zero);
                         } else {
                             gs_bfly<true>(v[r0][c], v[r0 + (1 << m)][c], w.x, w.y, q, two_q, zero);
@@ -236,7 +449,10 @@ column_gs_kernel(const uint32_t *__restrict__ in, uint32_t *__restrict__ out,
             V x;
             uint32_t *xs = reinterpret_cast<uint32_t *>(&x);
 #pragma unroll
-            for (int c = 0; c < VC; c++) xs[c] = min(v[r][c] - q, v[r][c]);
+            for (int c = 0; c < VC; c++) {
+                uint32_t x1 = CT ? min(v[r][c] - two_q, v[r][c]) : v[r][c];
+                xs[c] = min(x1 - q, x1);
+            }
             *reinterpret_cast<V *>(out + base + ((size_t) r << p.s0)) = x;
         }
     }
@@ -246,7 +462,7 @@ column_gs_kernel(const uint32_t *__restrict__ in, uint32_t *__restrict__ out,
 int tile_maps(CUtensorMap *lo, CUtensorMap *hi, const int32_t *base, size_t tiles);  // kernels_fused.cu
 
 int multi_prepare(nttb200_plan *p) {
-    if (p->logn < 13 || p->logn > 24) return NTTB200_ERR_UNSUPPORTED;
+    if (p->logn < 12 || p->logn > 24) return NTTB200_ERR_UNSUPPORTED;
     const uint32_t chunks = p->n >> 12;
     std::vector<uint2> host(p->n);
     NTTB200_CUDA(cudaMemcpy(host.data(), p->d_tw, sizeof(uint2) * p->n, cudaMemcpyDeviceToHost));
@@ -271,7 +487,11 @@ int multi_prepare(nttb200_plan *p) {
     }
     NTTB200_CUDA(cudaMalloc(&p->d_tw_tile, sizeof(uint4) * t.size()));
     NTTB200_CUDA(cudaMemcpy(p->d_tw_tile, t.data(), sizeof(uint4) * t.size(), cudaMemcpyHostToDevice));
-    NTTB200_CUDA(cudaFuncSetAttribute(tile_gs_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    NTTB200_CUDA(cudaFuncSetAttribute(tile_gs_kernel<false>,
+                                      cudaFuncAttributeMaxDynamicSharedMemorySize, kM_SmemBytes));
+    NTTB200_CUDA(cudaFuncSetAttribute(tile_gs_kernel<true>,
+                                      cudaFuncAttributeMaxDynamicSharedMemorySize, kM_SmemBytes));
+    NTTB200_CUDA(cudaFuncSetAttribute(tile_ct_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                       kM_SmemBytes));
     return NTTB200_OK;
 }
@@ -281,7 +501,7 @@ void multi_release(nttb200_plan *p) {
     p->d_tw_tile = nullptr;
 }
 
-template <int K, int VC>
+template <int K, int VC, bool CT>
 static int launch_column(nttb200_plan *p, const int32_t *in, int32_t *out, size_t batch, int s0,
                          cudaStream_t st) {
     ColParams cp;
@@ -293,46 +513,82 @@ static int launch_column(nttb200_plan *p, const int32_t *in, int32_t *out, size_
     uint64_t blocks = (cp.threads + 255) / 256;
     uint64_t cap = (uint64_t) p->sm_count * 64;
     int grid = (int) (blocks < cap ? blocks : cap);
-    column_gs_kernel<K, VC><<<grid, 256, 0, st>>>(reinterpret_cast<const uint32_t *>(in),
-                                                  reinterpret_cast<uint32_t *>(out), p->d_tw, cp);
+    column_kernel<K, VC, CT><<<grid, 256, 0, st>>>(reinterpret_cast<const uint32_t *>(in),
+                                                   reinterpret_cast<uint32_t *>(out), p->d_tw, cp);
     g_launches.fetch_add(1, std::memory_order_relaxed);
     NTTB200_CUDA(cudaGetLastError());
     return NTTB200_OK;
 }
 
 // stages [s0, s0+k) as one column pass; needs s0 >= 2 (128-bit columns) and aligned buffers
-int launch_column_pass(nttb200_plan *p, const int32_t *in, int32_t *out, size_t batch, int s0, int k,
-                       cudaStream_t st) {
+template <bool CT>
+static int column_pass_t(nttb200_plan *p, const int32_t *in, int32_t *out, size_t batch, int s0,
+                         int k, cudaStream_t st) {
     if (s0 < 2 || k < 1 || k > 6 || s0 + k > (int) p->logn) return NTTB200_ERR_UNSUPPORTED;
     if (((uintptr_t) in & 15u) || ((uintptr_t) out & 15u)) return NTTB200_ERR_UNSUPPORTED;
     switch (k) {
-        case 1: return launch_column<1, 4>(p, in, out, batch, s0, st);
-        case 2: return launch_column<2, 4>(p, in, out, batch, s0, st);
-        case 3: return launch_column<3, 4>(p, in, out, batch, s0, st);
-        case 4: return launch_column<4, 4>(p, in, out, batch, s0, st);
-        case 5: return launch_column<5, 2>(p, in, out, batch, s0, st);
-        default: return launch_column<6, 1>(p, in, out, batch, s0, st);
+        case 1: return launch_column<1, 4, CT>(p, in, out, batch, s0, st);
+        case 2: return launch_column<2, 4, CT>(p, in, out, batch, s0, st);
+        case 3: return launch_column<3, 4, CT>(p, in, out, batch, s0, st);
+        case 4: return launch_column<4, 4, CT>(p, in, out, batch, s0, st);
+        case 5: return launch_column<5, 2, CT>(p, in, out, batch, s0, st);
+        default: return launch_column<6, 1, CT>(p, in, out, batch, s0, st);
     }
 }
 
-static int launch_multi_gs_once(nttb200_plan *p, const int32_t *d_in, int32_t *d_out, size_t batch,
-                                cudaStream_t st) {
-    const uint32_t chunks = p->n >> 12;
-    const uint64_t tiles = (uint64_t) batch * chunks;
-    CUtensorMap map_lo, map_hi;
-    if (tile_maps(&map_lo, &map_hi, d_in, (size_t) tiles) != NTTB200_OK) {
-        return NTTB200_ERR_UNSUPPORTED;
-    }
+int launch_column_pass(nttb200_plan *p, const int32_t *in, int32_t *out, size_t batch, int s0, int k,
+                       cudaStream_t st) {
+    return column_pass_t<false>(p, in, out, batch, s0, k, st);
+}
+
+static uint32_t inv_mod_2_32(uint32_t q) {  // q odd
+    uint32_t x = q;                          // 3 correct bits; each Newton step doubles them
+    for (int i = 0; i < 5; i++) x *= 2u - q * x;
+    return x;
+}
+
+static TileParams tile_params(nttb200_plan *p, int32_t *d_out, size_t batch) {
     TileParams tp;
     tp.out = reinterpret_cast<uint32_t *>(d_out);
     tp.tw_tile = p->d_tw_tile;
     tp.batch = (uint32_t) batch;
-    tp.chunks = chunks;
+    tp.chunks = p->n >> 12;
     tp.q = p->q;
     tp.zero = 0;
+    tp.qinv = 0;
+    tp.scale = 0;
+    tp.scale_shoup = 0;
+    return tp;
+}
+
+static int tile_grid(nttb200_plan *p, uint64_t tiles) {
     uint64_t ctas = (tiles + kM_Teams - 1) / kM_Teams;
-    int grid = (int) (ctas < (uint64_t) p->sm_count ? ctas : (uint64_t) p->sm_count);
-    tile_gs_kernel<<<grid, kM_Threads, kM_SmemBytes, st>>>(map_lo, map_hi, tp);
+    return (int) (ctas < (uint64_t) p->sm_count ? ctas : (uint64_t) p->sm_count);
+}
+
+// d_b == nullptr: plain transform of d_in.  Otherwise the input is d_in (*) d_b and the
+// output is scaled by N^-1 (inverse transform of a negacyclic product).
+static int launch_multi_gs_once(nttb200_plan *p, const int32_t *d_in, const int32_t *d_b,
+                                int32_t *d_out, size_t batch, cudaStream_t st) {
+    const uint64_t tiles = (uint64_t) batch * (p->n >> 12);
+    CUtensorMap map_lo, map_hi, b_lo, b_hi;
+    if (tile_maps(&map_lo, &map_hi, d_in, (size_t) tiles) != NTTB200_OK) {
+        return NTTB200_ERR_UNSUPPORTED;
+    }
+    TileParams tp = tile_params(p, d_out, batch);
+    int grid = tile_grid(p, tiles);
+    if (d_b) {
+        if (tile_maps(&b_lo, &b_hi, d_b, (size_t) tiles) != NTTB200_OK) return NTTB200_ERR_UNSUPPORTED;
+        tp.qinv = inv_mod_2_32(p->q);
+        // the Montgomery product carries 2^-32: scale by N^-1 * 2^32 mod q
+        uint64_t sc = ((uint64_t) p->n_inv << 32) % p->q;
+        tp.scale = (uint32_t) sc;
+        tp.scale_shoup = (uint32_t) ((sc << 32) / p->q);
+        tile_gs_kernel<true><<<grid, kM_Threads, kM_SmemBytes, st>>>(map_lo, map_hi, b_lo, b_hi, tp);
+    } else {
+        tile_gs_kernel<false><<<grid, kM_Threads, kM_SmemBytes, st>>>(map_lo, map_hi, map_lo, map_hi,
+                                                                      tp);
+    }
     g_launches.fetch_add(1, std::memory_order_relaxed);
     NTTB200_CUDA(cudaGetLastError());
     // remaining stages 12..logn-1 in column passes of <= 6 stages, evenly split
@@ -372,10 +628,63 @@ int launch_multi_gs(nttb200_plan *p, const int32_t *d_in, int32_t *d_out, size_t
     }
     for (size_t b0 = 0; b0 < batch; b0 += sub) {
         size_t nb = batch - b0 < sub ? batch - b0 : sub;
-        int rc = launch_multi_gs_once(p, d_in + b0 * p->n, d_out + b0 * p->n, nb, st);
+        int rc = launch_multi_gs_once(p, d_in + b0 * p->n, nullptr, d_out + b0 * p->n, nb, st);
         if (rc != NTTB200_OK) return rc;
     }
     p->last_path = "tile_tma + column_passes";
+    return NTTB200_OK;
+}
+
+static bool multi_args_ok(nttb200_plan *p, const void *a, const void *b, size_t batch) {
+    const uint64_t tiles = (uint64_t) batch * (p->n >> 12);
+    return p->d_tw_tile && tiles <= 0x7fffffffull && batch <= 0xffffffffull &&
+           !((uintptr_t) a & 15u) && !((uintptr_t) b & 15u);
+}
+
+// inverse transform of the pointwise product of two transformed operands, scaled by
+// N^-1: the tail of a negacyclic multiplication (pointwise product and scaling fused
+// into the tile pass)
+int launch_multi_gs_dual(nttb200_plan *p, const int32_t *d_a, const int32_t *d_b, int32_t *d_out,
+                         size_t batch, cudaStream_t st) {
+    if (!multi_args_ok(p, d_a, d_out, batch) || ((uintptr_t) d_b & 15u) || !(p->q & 1u)) {
+        return NTTB200_ERR_UNSUPPORTED;
+    }
+    if (batch == 0) return NTTB200_OK;
+    int rc = launch_multi_gs_once(p, d_a, d_b, d_out, batch, st);
+    if (rc == NTTB200_OK) p->last_path = "tile_tma_dual + column_passes";
+    return rc;
+}
+
+// forward (CT) transform: column passes from the largest stride down to 2^12, then the
+// CT tile pass
+int launch_multi_ct(nttb200_plan *p, const int32_t *d_in, int32_t *d_out, size_t batch,
+                    cudaStream_t st) {
+    if (!multi_args_ok(p, d_in, d_out, batch)) return NTTB200_ERR_UNSUPPORTED;
+    if (batch == 0) return NTTB200_OK;
+    const int32_t *src = d_in;
+    int rest = (int) p->logn - 12;
+    int passes = (rest + 5) / 6;
+    int top = (int) p->logn;
+    for (int k = 0; k < passes; k++) {
+        int take = (rest + (passes - k) - 1) / (passes - k);
+        int rc = column_pass_t<true>(p, src, d_out, batch, top - take, take, st);
+        if (rc != NTTB200_OK) return rc;
+        src = d_out;
+        top -= take;
+        rest -= take;
+    }
+    const uint64_t tiles = (uint64_t) batch * (p->n >> 12);
+    CUtensorMap in_lo, in_hi, out_lo, out_hi;
+    if (tile_maps(&in_lo, &in_hi, src, (size_t) tiles) != NTTB200_OK ||
+        tile_maps(&out_lo, &out_hi, d_out, (size_t) tiles) != NTTB200_OK) {
+        return NTTB200_ERR_UNSUPPORTED;
+    }
+    TileParams tp = tile_params(p, d_out, batch);
+    tile_ct_kernel<<<tile_grid(p, tiles), kM_Threads, kM_SmemBytes, st>>>(in_lo, in_hi, out_lo, out_hi,
+                                                                          tp);
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+    NTTB200_CUDA(cudaGetLastError());
+    p->last_path = "column_passes_ct + tile_tma_ct";
     return NTTB200_OK;
 }
 

@@ -125,7 +125,7 @@ def test_gs_partial_depth_and_inplace(lib, oracle_mod, logn):
         assert np.array_equal(out, oracle_mod.ntt_gs(a, table, Q29, stage)), (logn, stage)
 
 
-@pytest.mark.parametrize("logn", [1, 4, 9, 12, 13, 16])
+@pytest.mark.parametrize("logn", [1, 4, 9, 12, 13, 16, 18, 19])
 def test_ct_vs_oracle(lib, oracle_mod, logn):
     n = 1 << logn
     rng = np.random.default_rng(3000 + logn)
@@ -178,7 +178,7 @@ def test_polymul_vs_schoolbook(lib, oracle_mod, logn):
         assert np.array_equal(d_b.cpu().numpy(), want)
 
 
-@pytest.mark.parametrize("logn", [12, 16])
+@pytest.mark.parametrize("logn", [12, 13, 14, 16, 19])
 def test_polymul_vs_oracle_pipeline(lib, oracle_mod, logn):
     n = 1 << logn
     rng = np.random.default_rng(7000 + logn)
