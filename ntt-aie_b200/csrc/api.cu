@@ -163,6 +163,14 @@ int nttb200_plan_create(nttb200_plan **out, int device, uint32_t logn, uint32_t 
         delete p;
         return cuda_fail(e, "cudaMemcpy(table)");
     }
+    {
+        int rc = generic_prepare();
+        if (rc != NTTB200_OK) {
+            cudaFree(p->d_tw);
+            delete p;
+            return rc;
+        }
+    }
     if (!(flags & NTTB200_FORCE_GENERIC)) {
         int rc = fused_prepare(p);
         if (rc == NTTB200_OK || rc == NTTB200_ERR_UNSUPPORTED) {

@@ -125,7 +125,10 @@ fused_gs4096_kernel(const __grid_constant__ CUtensorMap map_lo,
     const uint32_t bar_base = data_base + kF_Teams * kF_PolyBytes;
 
     const int tid = threadIdx.x;
-    const int team = tid >> 6;
+    // broadcast from lane 0 so the compiler knows the team index (and the whole
+    // per-team loop) is warp-uniform: q, 2q and the opaque zero then live in uniform
+    // registers instead of taking a third vector-register read port in every IADD3
+    const int team = __shfl_sync(0xffffffffu, tid >> 6, 0);
     const int j = tid & 63;
     const uint32_t q = prm.q, two_q = 2u * prm.q, zero = prm.zero;
 

@@ -48,6 +48,11 @@ stage_pass_kernel(const uint32_t *__restrict__ in, uint32_t *__restrict__ out,
     const uint32_t q = pp.q;
     const uint32_t logtile = pp.ns + pp.logc;
     const uint32_t tile = 1u << logtile;
+    // the tile's 2^ns - 1 twiddles, staged once per tile so the per-stage dependent
+    // global loads (one L2 round trip per stage) leave the critical path:
+    // ltw[(R >> (k+1)) + blk] = table[(n >> (s0+k+1)) + (high << (ns-k-1)) + blk]
+    uint2 *ltw = reinterpret_cast<uint2 *>(sm + tile);
+    const uint32_t rows = 1u << pp.ns;
     const uint32_t cmask = (1u << pp.logc) - 1u;
     const uint32_t lowhi_bits = pp.s0 - pp.logc;          // index bits between columns and rows
     const uint32_t tiles_per_poly_log = pp.logn - logtile;
@@ -68,19 +73,24 @@ stage_pass_kernel(const uint32_t *__restrict__ in, uint32_t *__restrict__ out,
             uint32_t r = e >> pp.logc, c = e & cmask;
             sm[e] = src[base | (r << pp.s0) | c];
         }
+        for (uint32_t e = threadIdx.x + 1; e < rows; e += kGenThreads) {
+            // entry e = hk + blk with hk = rows >> (k+1) the leading power of two of e
+            uint32_t lvl = 31u - __clz(e);               // hk = 1 << lvl, k = ns - 1 - lvl
+            uint32_t blk = e - (1u << lvl);
+            uint32_t k = pp.ns - 1u - lvl;
+            ltw[e] = __ldg(&tw[(n >> (pp.s0 + k + 1)) + (high << lvl) + blk]);
+        }
         __syncthreads();
 
         for (uint32_t kk = 0; kk < pp.ns; kk++) {
             const uint32_t k = CT ? (pp.ns - 1 - kk) : kk;  // CT: large stride first
-            const uint32_t s = pp.s0 + k;
-            const uint32_t h = n >> (s + 1);
+            const uint32_t hk = rows >> (k + 1);
             for (uint32_t b = threadIdx.x; b < (tile >> 1); b += kGenThreads) {
                 uint32_t rr = b >> pp.logc, c = b & cmask;
                 uint32_t r0 = ((rr >> k) << (k + 1)) | (rr & ((1u << k) - 1u));
                 uint32_t i0 = (r0 << pp.logc) | c;
                 uint32_t i1 = i0 + (1u << (k + pp.logc));
-                uint32_t blk = ((high << pp.ns) | r0) >> (k + 1);
-                uint2 w = __ldg(&tw[h + blk]);
+                uint2 w = ltw[hk + (r0 >> (k + 1))];
                 uint32_t x = sm[i0], y = sm[i1];
                 if (CT) {
                     uint32_t v = shoup_mul(y, w.x, w.y, q);
@@ -150,11 +160,22 @@ static int grid_for(uint64_t work_items, int sm_count, int per_sm) {
     return (int) (work_items < cap ? (work_items ? work_items : 1) : cap);
 }
 
+// per-device one-time setup (called from plan creation with the plan's device current):
+// 16 KiB of data + up to 32 KiB of staged twiddles per CTA
+int generic_prepare() {
+    NTTB200_CUDA(cudaFuncSetAttribute(stage_pass_kernel<true>,
+                                      cudaFuncAttributeMaxDynamicSharedMemorySize, 49152));
+    NTTB200_CUDA(cudaFuncSetAttribute(stage_pass_kernel<false>,
+                                      cudaFuncAttributeMaxDynamicSharedMemorySize, 49152));
+    return NTTB200_OK;
+}
+
 int launch_generic(nttb200_plan *p, const int32_t *d_in, int32_t *d_out, size_t batch, int sb,
                    int se, bool ct, bool permute_out, cudaStream_t st) {
     if (batch == 0 || sb >= se) {
         return NTTB200_OK;
     }
+
     // split [sb, se) into passes, each as deep as a 4096-word tile allows
     struct Pass {
         int s0, ns, logc;
@@ -189,7 +210,7 @@ int launch_generic(nttb200_plan *p, const int32_t *d_in, int32_t *d_out, size_t 
         pp.q = p->q;
         pp.permute = (permute_out && k == np - 1) ? 1u : 0u;
         pp.tiles = (uint64_t) batch << (p->logn - (uint32_t) (ps.ns + ps.logc));
-        size_t smem = sizeof(uint32_t) << (ps.ns + ps.logc);
+        size_t smem = (sizeof(uint32_t) << (ps.ns + ps.logc)) + (sizeof(uint2) << ps.ns);
         int grid = grid_for(pp.tiles, p->sm_count, 8);
         if (ct) {
             stage_pass_kernel<true><<<grid, kGenThreads, smem, st>>>(src, dst, p->d_tw, pp);

@@ -64,6 +64,7 @@ int cuda_fail(cudaError_t e, const char *what);
 // generic stage-pass kernels (kernels_generic.cu): stages [sb, se) of the GS
 // (ascending stride) or CT (descending stride) network; permute_out applies the
 // ans_order block permutation on the last pass's store.
+int generic_prepare();
 int launch_generic(nttb200_plan *p, const int32_t *d_in, int32_t *d_out, size_t batch, int sb,
                    int se, bool ct, bool permute_out, cudaStream_t st);
 int launch_pointwise(nttb200_plan *p, const int32_t *a, const int32_t *b, int32_t *c, size_t count,

@@ -14,6 +14,8 @@ __global__ void __launch_bounds__(1024) k(uint32_t *out, uint32_t a, uint32_t b,
 #pragma unroll
     for (int i = 0; i < NCH; i++) { x[i] = threadIdx.x * 7 + i + a; y[i] = x[i] * 3 + b; }
     const uint32_t two_q = 2 * q;
+    // per-thread copies the compiler cannot prove uniform (threadIdx.x >> 10 is 0)
+    const uint32_t qv = q + out[1 + (threadIdx.x & 1)], two_qv = 2 * qv, zv = zero + out[1 + (threadIdx.x & 3)];
     long long t0 = clock64();
 #pragma unroll 1
     for (int it = 0; it < ITERS; it++) {
@@ -33,6 +35,13 @@ __global__ void __launch_bounds__(1024) k(uint32_t *out, uint32_t a, uint32_t b,
                 uint32_t h = __umulhi(d, b);
                 x[i] = s;
                 y[i] = d * a - h * q;
+            } else if (V == 6) {                // full butterfly, q / 2q / zero in VECTOR registers
+                uint32_t s = x[i] + y[i] + zv;
+                uint32_t d = x[i] - y[i] + two_qv;
+                s = min(s - two_qv, s);
+                uint32_t h = __umulhi(d, b);
+                x[i] = s;
+                y[i] = d * a - h * qv;
             } else if (V == 3) {                // mulhi + one IMAD (h*q fused away)
                 uint32_t h = __umulhi(x[i], b);
                 x[i] = y[i] - h * q;
@@ -60,7 +69,7 @@ __global__ void __launch_bounds__(1024) k(uint32_t *out, uint32_t a, uint32_t b,
 template <int V>
 void run(int sms, int warps, const char *name, int fma_ops) {
     uint32_t *out; long long *clk, h;
-    cudaMalloc(&out, 4); cudaMalloc(&clk, 8);
+    cudaMalloc(&out, 64); cudaMemset(out, 0, 64); cudaMalloc(&clk, 8);
     k<V><<<sms, warps * 32>>>(out, 3, 0x9E3779B9u, 469762049u, 0, clk);
     k<V><<<sms, warps * 32>>>(out, 3, 0x9E3779B9u, 469762049u, 0, clk);
     cudaDeviceSynchronize();
@@ -76,7 +85,7 @@ int main() {
         run<0>(p.multiProcessorCount, w, "mulhi + 2 IMAD", 3);
         run<1>(p.multiProcessorCount, w, "sub + mulhi + 2 IMAD", 3);
         run<2>(p.multiProcessorCount, w, "full butterfly (uniform twiddle)", 3);
-        run<5>(p.multiProcessorCount, w, "full butterfly (register twiddle)", 3);
+        run<6>(p.multiProcessorCount, w, "full butterfly, constants in vector regs", 3);
         run<3>(p.multiProcessorCount, w, "mulhi + 1 IMAD", 2);
         run<4>(p.multiProcessorCount, w, "2 IMAD + add", 2);
     }
