@@ -16,6 +16,8 @@ __global__ void __launch_bounds__(1024) k(uint32_t *out, uint32_t a, uint32_t b,
     const uint32_t two_q = 2 * q;
     // per-thread copies the compiler cannot prove uniform (threadIdx.x >> 10 is 0)
     const uint32_t qv = q + out[1 + (threadIdx.x & 1)], two_qv = 2 * qv, zv = zero + out[1 + (threadIdx.x & 3)];
+    const uint32_t wv = a + out[2 + (threadIdx.x & 1)], wpv = b + out[4 + (threadIdx.x & 3)];
+    const uint32_t neg_q = 0u - q;
     long long t0 = clock64();
 #pragma unroll 1
     for (int it = 0; it < ITERS; it++) {
@@ -42,6 +44,29 @@ __global__ void __launch_bounds__(1024) k(uint32_t *out, uint32_t a, uint32_t b,
                 uint32_t h = __umulhi(d, b);
                 x[i] = s;
                 y[i] = d * a - h * qv;
+            } else if (V == 7) {                // per-thread (vector register) twiddles, y = d*w - h*q
+                uint32_t s = x[i] + y[i] + zero;
+                uint32_t d = x[i] - y[i] + two_q;
+                s = min(s - two_q, s);
+                uint32_t h = __umulhi(d, wpv);
+                x[i] = s;
+                y[i] = d * wv - h * q;
+            } else if (V == 8) {                // per-thread twiddles, y = h*(-q) + d*w
+                uint32_t s = x[i] + y[i] + zero;
+                uint32_t d = x[i] - y[i] + two_q;
+                s = min(s - two_q, s);
+                uint32_t h = __umulhi(d, wpv);
+                uint32_t t = d * wv;
+                x[i] = s;
+                y[i] = h * neg_q + t;
+            } else if (V == 9) {                // uniform twiddles, y = h*(-q) + d*w
+                uint32_t s = x[i] + y[i] + zero;
+                uint32_t d = x[i] - y[i] + two_q;
+                s = min(s - two_q, s);
+                uint32_t h = __umulhi(d, b);
+                uint32_t t = d * a;
+                x[i] = s;
+                y[i] = h * neg_q + t;
             } else if (V == 3) {                // mulhi + one IMAD (h*q fused away)
                 uint32_t h = __umulhi(x[i], b);
                 x[i] = y[i] - h * q;
@@ -81,11 +106,14 @@ void run(int sms, int warps, const char *name, int fma_ops) {
 
 int main() {
     cudaDeviceProp p; cudaGetDeviceProperties(&p, 0);
-    for (int w : {4, 8, 16, 32}) {
+    for (int w : {16, 32}) {
         run<0>(p.multiProcessorCount, w, "mulhi + 2 IMAD", 3);
         run<1>(p.multiProcessorCount, w, "sub + mulhi + 2 IMAD", 3);
         run<2>(p.multiProcessorCount, w, "full butterfly (uniform twiddle)", 3);
         run<6>(p.multiProcessorCount, w, "full butterfly, constants in vector regs", 3);
+        run<7>(p.multiProcessorCount, w, "vector twiddles, d*w - h*q", 3);
+        run<8>(p.multiProcessorCount, w, "vector twiddles, h*(-q) + d*w", 3);
+        run<9>(p.multiProcessorCount, w, "uniform twiddles, h*(-q) + d*w", 3);
         run<3>(p.multiProcessorCount, w, "mulhi + 1 IMAD", 2);
         run<4>(p.multiProcessorCount, w, "2 IMAD + add", 2);
     }
