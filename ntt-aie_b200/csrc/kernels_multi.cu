@@ -470,7 +470,7 @@ column_kernel(const uint32_t *__restrict__ in, uint32_t *__restrict__ out,
 int tile_maps(CUtensorMap *lo, CUtensorMap *hi, const int32_t *base, size_t tiles);  // kernels_fused.cu
 
 int multi_prepare(nttb200_plan *p) {
-    if (p->logn < 12 || p->logn > 24) return NTTB200_ERR_UNSUPPORTED;
+    if (p->logn < 12 || p->logn > 26) return NTTB200_ERR_UNSUPPORTED;
     const uint32_t chunks = p->n >> 12;
     std::vector<uint2> host(p->n);
     NTTB200_CUDA(cudaMemcpy(host.data(), p->d_tw, sizeof(uint2) * p->n, cudaMemcpyDeviceToHost));

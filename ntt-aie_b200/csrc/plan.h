@@ -35,7 +35,7 @@ struct nttb200_plan {
     uint2 *d_tw = nullptr;   // [N] (w, floor(w*2^32/q)), golden index rule table[h+i]
     // fused-kernel twiddle staging (built lazily per kernel family)
     uint4 *d_tw_r1 = nullptr;        // round-1 per-thread twiddles, kernel-private order
-    uint4 *d_tw_tile = nullptr;      // [N/4096][32][65] tile-pass twiddles (logn 13..24)
+    uint4 *d_tw_tile = nullptr;      // [N/4096][32][65] tile-pass twiddles (logn 12..26)
     nttb200::UniformTw uni_gs{};     // round-2 uniform twiddles, GS network
     int sm_count = 148;
     const char *last_path = "none";
@@ -80,7 +80,7 @@ void fused_release(nttb200_plan *p);
 int launch_fused_gs(nttb200_plan *p, const int32_t *d_in, int32_t *d_out, size_t batch,
                     bool permute_out, cudaStream_t st);
 
-// tile pass + column passes for logn 13..24 (kernels_multi.cu)
+// tile pass + column passes for logn 12..26 (kernels_multi.cu)
 int multi_prepare(nttb200_plan *p);
 void multi_release(nttb200_plan *p);
 int launch_multi_gs(nttb200_plan *p, const int32_t *d_in, int32_t *d_out, size_t batch,
