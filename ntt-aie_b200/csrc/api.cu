@@ -174,6 +174,7 @@ int nttb200_plan_create(nttb200_plan **out, int device, uint32_t logn, uint32_t 
     }
     if (!(flags & NTTB200_FORCE_GENERIC)) {
         int rc = fused_prepare(p);
+        if (rc == NTTB200_ERR_UNSUPPORTED) rc = small_prepare(p);
         if (rc == NTTB200_OK || rc == NTTB200_ERR_UNSUPPORTED) {
             int rc2 = multi_prepare(p);
             if (rc2 != NTTB200_ERR_UNSUPPORTED) rc = rc2;
@@ -220,6 +221,18 @@ static int run_gs(nttb200_plan *p, const int32_t *d_in, int32_t *d_out, size_t b
             rc = launch_multi_gs(p, d_in, d_out, batch, st);
             if (rc != NTTB200_ERR_UNSUPPORTED) return rc;
         }
+        size_t done = 0;
+        rc = launch_small_gs(p, d_in, d_out, batch, permute, st, &done);
+        if (rc == NTTB200_OK) {
+            if (done == batch) return rc;
+            // ragged tail (< one 2048-coefficient block) through the generic pass
+            const char *path = p->last_path;
+            rc = launch_generic(p, d_in + done * p->n, d_out + done * p->n, batch - done, 0,
+                                (int) p->logn, false, permute, st);
+            p->last_path = path;
+            return rc;
+        }
+        if (rc != NTTB200_ERR_UNSUPPORTED) return rc;
     }
     p->last_path = "generic_stage_pass";
     int se = full ? (int) p->logn : stage_limit + 1;

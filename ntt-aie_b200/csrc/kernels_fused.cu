@@ -250,17 +250,22 @@ static EncodeTiledFn encode_tiled() {
 
 // view of the batch for TMA: dim0 = 32 words of one half-row, dim1 = 64 rows
 // (stride 256 B), dim2 = polynomial (stride 16 KiB); box = one half of one polynomial
-static int make_half_map(CUtensorMap *map, const int32_t *base, size_t batch) {
+// (general form: `rows` rows of 64 words per tile, rows*256 bytes per tile)
+int encode_tile_map(CUtensorMap *map, const int32_t *base, uint32_t rows, size_t batch) {
     EncodeTiledFn enc = encode_tiled();
     if (!enc) return NTTB200_ERR_CUDA;
-    cuuint64_t dims[3] = {32, 64, (cuuint64_t) batch};
-    cuuint64_t strides[2] = {256, (cuuint64_t) kF_PolyBytes};
-    cuuint32_t box[3] = {32, 64, 1};
+    cuuint64_t dims[3] = {32, rows, (cuuint64_t) batch};
+    cuuint64_t strides[2] = {256, (cuuint64_t) rows * 256};
+    cuuint32_t box[3] = {32, rows, 1};
     cuuint32_t estr[3] = {1, 1, 1};
     CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_INT32, 3, (void *) base, dims, strides, box, estr,
                      CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
                      CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     return r == CUDA_SUCCESS ? NTTB200_OK : NTTB200_ERR_CUDA;
+}
+
+static int make_half_map(CUtensorMap *map, const int32_t *base, size_t batch) {
+    return encode_tile_map(map, base, 64, batch);
 }
 
 // both half-tile maps of a buffer of `tiles` contiguous 4096-word tiles

@@ -1,0 +1,283 @@
+// kernels_small.cu -- whole-transform register-radix kernel for N = 2^9 .. 2^11,
+// which includes the reference's own default N = 2048 (reference src/test.cpp:66,
+// src/aie2.py:14).
+//
+// One WARP owns a block of 2048 consecutive coefficients = 2^(11-logn) polynomials:
+//   TMA (128B swizzle) HBM -> shared, 8 KiB per warp
+//   round 1  lane j owns a[64j .. 64j+63]: golden stages 0-5 in registers, its 63
+//            private (w, w') pairs from a shared-memory table (conflict-free LDS.128)
+//   exchange through the same buffer, warp-synchronous (__syncwarp, no block barrier)
+//   round 2  lane j owns columns 2j, 2j+1 of all 32 rows (LDS.64): the remaining
+//            logn-6 stages pair rows; twiddles depend only on the register index, so
+//            they are kernel parameters (constant-bank / uniform-register operands)
+//   store    canonicalise, one 256 B row per STG.64 warp instruction
+// 16 warps per CTA, one persistent CTA per SM; the next block's TMA load is issued as
+// soon as round 2 has pulled the current one out of shared memory.
+// Butterflies and laziness as in kernels_fused.cu; bit-exact against the golden.
+#include <cuda.h>
+
+#include <vector>
+
+#include "fused_common.cuh"
+#include "plan.h"
+
+namespace nttb200 {
+
+constexpr int kS_Warps = 16;
+constexpr int kS_Threads = kS_Warps * 32;
+constexpr int kS_BlockBytes = 2048 * 4;                 // one warp's block
+constexpr int kS_TwBytes = 32 * 32 * 16;                // [32 slots][32 lanes] uint4
+constexpr int kS_SmemBytes = kS_TwBytes + kS_Warps * kS_BlockBytes + 16 * 8 + 1024;
+
+struct SmallParams {
+    uint32_t *out;
+    const uint4 *tw_r1;   // [32 slots][32 lanes]
+    uint64_t blocks;      // 2048-coefficient blocks in the batch
+    uint32_t q;
+    uint32_t zero;
+};
+
+// round-1 stage (same slot scheme as kernels_fused.cu, 32 lanes per slot)
+template <int S>
+__device__ __forceinline__ void small_r1_stage(uint32_t (&v)[64], uint32_t tw_addr, uint32_t q,
+                                               uint32_t two_q, uint32_t zero) {
+    constexpr int kBlocks = 32 >> S;
+    constexpr int kSlot0 = 32 - (kBlocks >= 2 ? kBlocks : 1);
+    constexpr int kStride = 1 << S;
+#pragma unroll
+    for (int b = 0; b < kBlocks; b += 2) {
+        uint4 t = lds128(tw_addr + (kSlot0 + b / 2) * (32 * 16));
+#pragma unroll
+        for (int e = 0; e < kStride; e++) {
+            int i0 = b * 2 * kStride + e;
+            gs_bfly<(S > 0)>(v[i0], v[i0 + kStride], t.x, t.y, q, two_q, zero);
+        }
+        if (kBlocks >= 2) {
+#pragma unroll
+            for (int e = 0; e < kStride; e++) {
+                int i0 = (b + 1) * 2 * kStride + e;
+                gs_bfly<(S > 0)>(v[i0], v[i0 + kStride], t.z, t.w, q, two_q, zero);
+            }
+        }
+    }
+}
+
+// round-2 stage K on registers v[2*row + col]: pairs rows i and i + 2^K inside each
+// polynomial (RP = 2^(LOGN-6) rows per polynomial); twiddle table[(RP >> (K+1)) + blk]
+template <int LOGN, int K>
+__device__ __forceinline__ void small_r2_stage(uint32_t (&v)[64], const UniformTw &u, uint32_t q,
+                                               uint32_t two_q, uint32_t zero) {
+    constexpr int RP = 1 << (LOGN - 6);
+#pragma unroll
+    for (int i = 0; i < 32; i++) {
+        if (i & (1 << K)) continue;
+        const int blk = (i & (RP - 1)) >> (K + 1);
+        const uint32_t w = u.w[(RP >> (K + 1)) + blk], wp = u.wp[(RP >> (K + 1)) + blk];
+#pragma unroll
+        for (int c = 0; c < 2; c++) {
+            gs_bfly<true>(v[2 * i + c], v[2 * (i + (1 << K)) + c], w, wp, q, two_q, zero);
+        }
+    }
+}
+
+template <int LOGN, bool PERMUTE>
+__global__ void __launch_bounds__(kS_Threads, 1)
+fused_gs_small_kernel(const __grid_constant__ CUtensorMap map_lo,
+                      const __grid_constant__ CUtensorMap map_hi,
+                      const __grid_constant__ UniformTw uni, const SmallParams prm) {
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    const uint32_t tw_base = smem_base;
+    const uint32_t data_base = smem_base + kS_TwBytes;
+    const uint32_t bar_base = data_base + kS_Warps * kS_BlockBytes;
+    const int tid = threadIdx.x;
+    const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);  // warp-uniform for the compiler
+    const int j = tid & 31;
+    const uint32_t q = prm.q, two_q = 2u * prm.q, zero = prm.zero;
+
+    for (int i = tid; i < 32 * 32; i += kS_Threads) {
+        uint4 t = __ldg(prm.tw_r1 + i);
+        sts128(tw_base + i * 16, t.x, t.y, t.z, t.w);
+    }
+    if (tid < kS_Warps) mbar_init(bar_base + tid * 8, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    __syncthreads();
+
+    const uint32_t buf = data_base + warp * kS_BlockBytes;
+    const uint32_t bar = bar_base + warp * 8;
+    const uint64_t stride = (uint64_t) gridDim.x * kS_Warps;
+    uint64_t blk = (uint64_t) blockIdx.x * kS_Warps + warp;
+    uint32_t parity = 0;
+    if (j == 0 && blk < prm.blocks) {
+        mbar_expect_tx(bar, kS_BlockBytes);
+        tma_load_3d(buf, &map_lo, bar, 0, 0, (int) blk);
+        tma_load_3d(buf + kS_BlockBytes / 2, &map_hi, bar, 0, 0, (int) blk);
+    }
+    // buffer layout: two halves of [32 rows][32 words]; row r / half h holds
+    // a[64r + 32h .. +31]; 16-byte chunk index XOR (r & 7)
+    const uint32_t r1_row = buf + j * 128;
+    const uint32_t r1_xor = (j & 7) << 4;
+    // round 2: lane j owns words 2j, 2j+1 of every 64-word row: half j>>4, word 2(j&15)
+    const uint32_t r2_col = buf + (j >> 4) * (kS_BlockBytes / 2) + (j & 1) * 8;
+    const uint32_t r2_chunk = ((j & 15) >> 1) << 4;
+    const uint32_t tw_addr = tw_base + j * 16;
+
+    for (; blk < prm.blocks; blk += stride) {
+        uint32_t v[64];
+        mbar_wait(bar, parity);
+        parity ^= 1;
+#pragma unroll
+        for (int c = 0; c < 16; c++) {
+            uint4 t = lds128(r1_row + (c >> 3) * (kS_BlockBytes / 2) + (((c & 7) << 4) ^ r1_xor));
+            v[4 * c + 0] = t.x;
+            v[4 * c + 1] = t.y;
+            v[4 * c + 2] = t.z;
+            v[4 * c + 3] = t.w;
+        }
+        small_r1_stage<0>(v, tw_addr, q, two_q, zero);
+        small_r1_stage<1>(v, tw_addr, q, two_q, zero);
+        small_r1_stage<2>(v, tw_addr, q, two_q, zero);
+        small_r1_stage<3>(v, tw_addr, q, two_q, zero);
+        small_r1_stage<4>(v, tw_addr, q, two_q, zero);
+        small_r1_stage<5>(v, tw_addr, q, two_q, zero);
+#pragma unroll
+        for (int c = 0; c < 16; c++) {
+            sts128(r1_row + (c >> 3) * (kS_BlockBytes / 2) + (((c & 7) << 4) ^ r1_xor), v[4 * c],
+                   v[4 * c + 1], v[4 * c + 2], v[4 * c + 3]);
+        }
+        __syncwarp();
+#pragma unroll
+        for (int i = 0; i < 32; i++) {
+            uint32_t addr = r2_col + i * 128 + (r2_chunk ^ ((i & 7) << 4));
+            asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];"
+                         : "=r"(v[2 * i]), "=r"(v[2 * i + 1])
+                         : "r"(addr));
+        }
+        fence_proxy_async();
+        __syncwarp();
+        const uint64_t next = blk + stride;
+        if (j == 0 && next < prm.blocks) {
+            mbar_expect_tx(bar, kS_BlockBytes);
+            tma_load_3d(buf, &map_lo, bar, 0, 0, (int) next);
+            tma_load_3d(buf + kS_BlockBytes / 2, &map_hi, bar, 0, 0, (int) next);
+        }
+        if (LOGN > 6) small_r2_stage<LOGN, 0>(v, uni, q, two_q, zero);
+        if (LOGN > 7) small_r2_stage<LOGN, 1>(v, uni, q, two_q, zero);
+        if (LOGN > 8) small_r2_stage<LOGN, 2>(v, uni, q, two_q, zero);
+        if (LOGN > 9) small_r2_stage<LOGN, 3>(v, uni, q, two_q, zero);
+        if (LOGN > 10) small_r2_stage<LOGN, 4>(v, uni, q, two_q, zero);
+
+        // register (row i, col c) is coefficient 64 i + 2j + c of the block
+        uint32_t *dst = prm.out + blk * 2048 + 2 * j;
+#pragma unroll
+        for (int i = 0; i < 32; i++) {
+            int row = i;
+            if (PERMUTE && LOGN == 11) {
+                // ans_order on the top four of the 11 index bits = row bits 1..4
+                int b = i >> 1;
+                b = ((b & 0x5) << 1) | ((b & 0xA) >> 1);
+                row = (b << 1) | (i & 1);
+            }
+            uint2 o;
+            o.x = min(v[2 * i] - q, v[2 * i]);
+            o.y = min(v[2 * i + 1] - q, v[2 * i + 1]);
+            *reinterpret_cast<uint2 *>(dst + row * 64) = o;
+        }
+    }
+}
+
+// --------------------------------------------------------------------- host side
+int encode_tile_map(CUtensorMap *map, const int32_t *base, uint32_t rows, size_t blocks);  // kernels_fused.cu
+
+template <int LOGN>
+static int small_set_attr() {
+    NTTB200_CUDA(cudaFuncSetAttribute(fused_gs_small_kernel<LOGN, false>,
+                                      cudaFuncAttributeMaxDynamicSharedMemorySize, kS_SmemBytes));
+    NTTB200_CUDA(cudaFuncSetAttribute(fused_gs_small_kernel<LOGN, true>,
+                                      cudaFuncAttributeMaxDynamicSharedMemorySize, kS_SmemBytes));
+    return NTTB200_OK;
+}
+
+int small_prepare(nttb200_plan *p) {
+    if (p->logn < 9 || p->logn > 11) return NTTB200_ERR_UNSUPPORTED;
+    const uint32_t n = p->n;
+    const int tpp = (int) (n >> 6);  // lanes per polynomial
+    std::vector<uint2> host(n);
+    NTTB200_CUDA(cudaMemcpy(host.data(), p->d_tw, sizeof(uint2) * n, cudaMemcpyDeviceToHost));
+    // stage s block b of lane j: table[(n >> (s+1)) + (j % tpp)*(32 >> s) + b]
+    std::vector<uint4> r1(32 * 32);
+    for (int s = 0; s < 6; s++) {
+        const int blocks = 32 >> s;
+        const int slot0 = 32 - (blocks >= 2 ? blocks : 1);
+        for (int j = 0; j < 32; j++) {
+            size_t base = (size_t) (n >> (s + 1)) + (size_t) (j % tpp) * blocks;
+            for (int b = 0; b < blocks; b += 2) {
+                uint2 t0 = host[base + b];
+                uint2 t1 = blocks >= 2 ? host[base + b + 1] : make_uint2(0, 0);
+                r1[(size_t) (slot0 + b / 2) * 32 + j] = make_uint4(t0.x, t0.y, t1.x, t1.y);
+            }
+        }
+    }
+    NTTB200_CUDA(cudaMalloc(&p->d_tw_r1, sizeof(uint4) * r1.size()));
+    NTTB200_CUDA(cudaMemcpy(p->d_tw_r1, r1.data(), sizeof(uint4) * r1.size(),
+                            cudaMemcpyHostToDevice));
+    for (int i = 0; i < 64; i++) {
+        p->uni_gs.w[i] = i < tpp ? host[i].x : 0;
+        p->uni_gs.wp[i] = i < tpp ? host[i].y : 0;
+    }
+    switch (p->logn) {
+        case 9: return small_set_attr<9>();
+        case 10: return small_set_attr<10>();
+        default: return small_set_attr<11>();
+    }
+}
+
+template <int LOGN>
+static void small_launch_t(bool permute, int grid, cudaStream_t st, const CUtensorMap &lo,
+                           const CUtensorMap &hi, const UniformTw &uni, const SmallParams &prm) {
+    if (permute) {
+        fused_gs_small_kernel<LOGN, true><<<grid, kS_Threads, kS_SmemBytes, st>>>(lo, hi, uni, prm);
+    } else {
+        fused_gs_small_kernel<LOGN, false><<<grid, kS_Threads, kS_SmemBytes, st>>>(lo, hi, uni, prm);
+    }
+}
+
+// Handles the largest multiple of 2048 coefficients; *done_polys tells the caller how
+// many polynomials were transformed (the ragged tail goes through the generic pass).
+int launch_small_gs(nttb200_plan *p, const int32_t *d_in, int32_t *d_out, size_t batch,
+                    bool permute_out, cudaStream_t st, size_t *done_polys) {
+    *done_polys = 0;
+    if (p->logn < 9 || p->logn > 11 || !p->d_tw_r1) return NTTB200_ERR_UNSUPPORTED;
+    if (permute_out && p->logn != 11) return NTTB200_ERR_UNSUPPORTED;
+    const size_t per_block = (size_t) 2048 >> p->logn;
+    const size_t blocks = batch / per_block;
+    if (blocks == 0 || blocks > 0x7fffffffull || ((uintptr_t) d_in & 15u) ||
+        ((uintptr_t) d_out & 7u)) {
+        return NTTB200_ERR_UNSUPPORTED;
+    }
+    CUtensorMap lo, hi;
+    if (encode_tile_map(&lo, d_in, 32, blocks) != NTTB200_OK ||
+        encode_tile_map(&hi, d_in + 32, 32, blocks) != NTTB200_OK) {
+        return NTTB200_ERR_UNSUPPORTED;
+    }
+    SmallParams prm;
+    prm.out = reinterpret_cast<uint32_t *>(d_out);
+    prm.tw_r1 = p->d_tw_r1;
+    prm.blocks = blocks;
+    prm.q = p->q;
+    prm.zero = 0;
+    uint64_t ctas = (blocks + kS_Warps - 1) / kS_Warps;
+    int grid = (int) (ctas < (uint64_t) p->sm_count ? ctas : (uint64_t) p->sm_count);
+    switch (p->logn) {
+        case 9: small_launch_t<9>(permute_out, grid, st, lo, hi, p->uni_gs, prm); break;
+        case 10: small_launch_t<10>(permute_out, grid, st, lo, hi, p->uni_gs, prm); break;
+        default: small_launch_t<11>(permute_out, grid, st, lo, hi, p->uni_gs, prm); break;
+    }
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+    NTTB200_CUDA(cudaGetLastError());
+    p->last_path = "fused_gs_small_warp_tma";
+    *done_polys = blocks * per_block;
+    return NTTB200_OK;
+}
+
+}  // namespace nttb200

@@ -80,6 +80,11 @@ void fused_release(nttb200_plan *p);
 int launch_fused_gs(nttb200_plan *p, const int32_t *d_in, int32_t *d_out, size_t batch,
                     bool permute_out, cudaStream_t st);
 
+// warp-per-block kernel for N = 2^9..2^11 (kernels_small.cu)
+int small_prepare(nttb200_plan *p);
+int launch_small_gs(nttb200_plan *p, const int32_t *d_in, int32_t *d_out, size_t batch,
+                    bool permute_out, cudaStream_t st, size_t *done_polys);
+
 // tile pass + column passes for logn 12..26 (kernels_multi.cu)
 int multi_prepare(nttb200_plan *p);
 void multi_release(nttb200_plan *p);

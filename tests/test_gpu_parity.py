@@ -335,3 +335,25 @@ def test_large_n_multi_pass_path(lib, oracle_mod, logn):
         assert np.array_equal(out, oracle_mod.ntt_gs(a, table, Q29)), (logn, batch)
         out, _ = run_gs(lib, a, table, Q29, inplace=True)
         assert np.array_equal(out, oracle_mod.ntt_gs(a, table, Q29)), (logn, batch, "in place")
+
+
+@pytest.mark.parametrize("logn", [9, 10, 11])
+def test_small_n_warp_kernel_ragged_batches(lib, oracle_mod, logn):
+    """N = 512..2048 run one warp per 2048-coefficient block; batches that are not a
+    multiple of the block (tail through the generic pass), in place, 12-bit and
+    30-bit moduli, AIE device order at N=2048 with a batch."""
+    n = 1 << logn
+    rng = np.random.default_rng(11000 + logn)
+    for p in (3329, Q30):
+        table = rng.integers(0, p, n, dtype=np.int32)
+        a = rng.integers(0, p, (70, n), dtype=np.int32)
+        want = oracle_mod.ntt_gs(a, table, p)
+        for batch in (1, 2, 3, 4, 5, 31, 32, 33, 70):
+            out, path = run_gs(lib, a[:batch], table, p, inplace=(batch % 2 == 0))
+            assert np.array_equal(out, want[:batch]), (logn, p, batch, path)
+    if logn == 11:
+        g = load_golden("default_n2048_p3329.npz")
+        a = np.stack([g["a"], (g["a"] * 7) % 3329, np.zeros(2048, np.int32)]).astype(np.int32)
+        out, path = run_gs(lib, a, g["roots"], 3329, flags=1)
+        assert "small" in path
+        assert np.array_equal(out, oracle_mod.ans_order_permute(oracle_mod.ntt_gs(a, g["roots"], 3329)))
