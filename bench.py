@@ -71,7 +71,7 @@ def ncu_traffic_per_launch():
 class ClockSampler(threading.Thread):
     """Samples SM clocks and throttle reasons while the timed region runs."""
 
-    def __init__(self, index: int, period_s: float = 0.1):
+    def __init__(self, index: int, period_s: float = 0.002):
         super().__init__(daemon=True)
         self.index, self.period = index, period_s
         self.samples, self.reasons, self.max_mhz = [], set(), None
@@ -328,7 +328,7 @@ def run_ours(args) -> None:
 def main() -> None:
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=100)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", choices=["ours", "reference"], default="ours")
     ap.add_argument("--batch", type=int, default=BATCH, help="polynomials per GPU per step")
