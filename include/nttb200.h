@@ -121,6 +121,20 @@ NTTB200_API int nttb200_gs_stage_range(nttb200_plan *plan, const int32_t *d_in, 
                                        size_t batch, int stage_begin, int stage_end,
                                        void *cuda_stream);
 
+/* The exchange step of the multi-GPU split fused into the last pass: stages
+ * [stage_begin, stage_end = logn) of ONE length-N vector d_buf (this rank's shard or
+ * its post-transpose rows), whose results are stored straight into the peers that own
+ * them after the transpose -- element idx goes to peer idx >> (logn - log2 world) at
+ * offset rank*2^(logn-log2 world) + (idx mod 2^(logn-log2 world)).  peer_bufs[k] is a
+ * device pointer to rank k's receive buffer mapped into this process (CUDA IPC /
+ * symmetric memory; peer_bufs[rank] is the local one).  The successor of the
+ * reference's cross-tile butterflies that write into a neighbour tile's memory
+ * (src/aie2.py:184-187,226-229).  The caller synchronises the ranks before the
+ * receive buffers are read.  world: power of two <= 16. */
+NTTB200_API int nttb200_gs_stage_range_scatter(nttb200_plan *plan, int32_t *d_buf, int stage_begin,
+                                               int stage_end, void *const *peer_bufs, int world,
+                                               int rank, void *cuda_stream);
+
 /* Host-buffer form of the hot path: what the reference host does around one
  * launch -- sync inputs to the device, run, sync the output back
  * (src/test.cpp:148-151,159-168,181-190).  h_in/h_out are HOST pointers

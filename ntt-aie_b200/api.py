@@ -56,6 +56,9 @@ def load_library():
         "nttb200_ct_batch": (ctypes.c_int, [vp, vp, vp, sz, ctypes.c_int, vp]),
         "nttb200_gs_stage_range": (ctypes.c_int, [vp, vp, vp, sz, ctypes.c_int, ctypes.c_int, vp]),
         "nttb200_gs_host": (ctypes.c_int, [vp, vp, vp, sz, ctypes.c_int]),
+        "nttb200_gs_stage_range_scatter": (ctypes.c_int, [vp, vp, ctypes.c_int, ctypes.c_int,
+                                                          ctypes.POINTER(vp), ctypes.c_int,
+                                                          ctypes.c_int, vp]),
         "nttb200_pointwise": (ctypes.c_int, [vp, vp, vp, vp, sz, vp]),
         "nttb200_scale": (ctypes.c_int, [vp, vp, vp, sz, i32, vp]),
         "nttb200_polymul_negacyclic": (ctypes.c_int, [vp, vp, vp, vp, vp, sz, vp]),
@@ -78,7 +81,7 @@ def load_library():
 EXPORTED_SYMBOLS = (
     "nttb200_make_roots", "nttb200_make_bitrev_table", "nttb200_powmod", "nttb200_plan_create",
     "nttb200_plan_destroy", "nttb200_gs_batch", "nttb200_ct_batch", "nttb200_gs_stage_range",
-    "nttb200_gs_host", "nttb200_pointwise", "nttb200_scale", "nttb200_polymul_negacyclic",
+    "nttb200_gs_host", "nttb200_gs_stage_range_scatter", "nttb200_pointwise", "nttb200_scale", "nttb200_polymul_negacyclic",
     "nttb200_strerror", "nttb200_last_error", "nttb200_kernel_launches", "nttb200_plan_last_path",
     "nttb200_plan_logn", "nttb200_plan_modulus", "nttb200_version",
 )
@@ -197,6 +200,16 @@ class Plan:
         _check(self._lib.nttb200_gs_stage_range(self._h, _addr(d_in), _addr(d_out), batch,
                                                 stage_begin, stage_end, _stream(stream)),
                "gs_stage_range")
+
+    def gs_stage_range_scatter(self, d_buf, stage_begin: int, stage_end: int, peer_ptrs, rank: int,
+                               stream=None) -> None:
+        """Stages [stage_begin, logn) of one vector with the results stored into the peers'
+        receive buffers (the all-to-all fused into the last pass)."""
+        world = len(peer_ptrs)
+        arr = (ctypes.c_void_p * world)(*[int(x) for x in peer_ptrs])
+        _check(self._lib.nttb200_gs_stage_range_scatter(self._h, _addr(d_buf), stage_begin,
+                                                        stage_end, arr, world, rank,
+                                                        _stream(stream)), "gs_stage_range_scatter")
 
     def gs_host(self, h_in, h_out, batch: int, stage: int = -1) -> None:
         """Host buffers in, host buffers out (the reference's BO sync + launch + sync,

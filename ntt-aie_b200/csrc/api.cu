@@ -299,6 +299,14 @@ int nttb200_gs_stage_range(nttb200_plan *p, const int32_t *d_in, int32_t *d_out,
     return launch_generic(p, d_in, d_out, batch, stage_begin, stage_end, false, false, st);
 }
 
+int nttb200_gs_stage_range_scatter(nttb200_plan *p, int32_t *d_buf, int stage_begin, int stage_end,
+                                   void *const *peer_bufs, int world, int rank, void *stream) {
+    if (!p || !d_buf || !peer_bufs) return NTTB200_ERR_INVALID_ARG;
+    DeviceGuard guard(p->device);
+    return launch_gs_range_scatter(p, d_buf, stage_begin, stage_end, peer_bufs, world, rank,
+                                   (cudaStream_t) stream);
+}
+
 static int host_prepare(nttb200_plan *p) {
     if (p->host_ready) return NTTB200_OK;
     // staging buffers of 32 MiB each: deep enough to hide the PCIe latency,

@@ -394,15 +394,28 @@ struct ColParams {
     uint64_t threads; // total logical threads = batch * N / (2^K * VC)
 };
 
+// Scatter store of the exchange step of the multi-GPU split (one transform, batch 1):
+// instead of writing its result in place, the pass writes element idx of this rank's
+// length-2^logn vector straight into the peer that owns it after the transpose,
+//     rank' = idx >> (logn - log_g),  offset' = rank * 2^(logn-log_g) + (idx & (2^(logn-log_g) - 1)),
+// through NVLink peer pointers -- the all-to-all fused into the last local pass
+// (the GPU analogue of the reference's neighbour-memory butterflies,
+// src/aie2.py:184-187, which also write into another tile's memory).
+struct ScatterParams {
+    uint32_t *peer[16];
+    uint32_t log_g;
+    uint32_t rank;
+};
+
 template <int VC> struct VecT;
 template <> struct VecT<1> { using type = uint32_t; };
 template <> struct VecT<2> { using type = uint2; };
 template <> struct VecT<4> { using type = uint4; };
 
-template <int K, int VC, bool CT>
+template <int K, int VC, bool CT, bool SCATTER>
 __global__ void __launch_bounds__(256)
 column_kernel(const uint32_t *__restrict__ in, uint32_t *__restrict__ out,
-              const uint2 *__restrict__ tw, const ColParams p) {
+              const uint2 *__restrict__ tw, const ColParams p, const ScatterParams sp) {
     constexpr int R = 1 << K;
     using V = typename VecT<VC>::type;
     const uint32_t q = p.q, two_q = 2u * p.q, zero = p.zero;
@@ -461,7 +474,15 @@ column_kernel(const uint32_t *__restrict__ in, uint32_t *__restrict__ out,
                 uint32_t x1 = CT ? min(v[r][c] - two_q, v[r][c]) : v[r][c];
                 xs[c] = min(x1 - q, x1);
             }
-            *reinterpret_cast<V *>(out + base + ((size_t) r << p.s0)) = x;
+            if (SCATTER) {
+                const uint32_t idx = (uint32_t) (base + ((size_t) r << p.s0));  // batch is 1
+                const uint32_t slice_bits = p.logn - sp.log_g;
+                uint32_t *dst = sp.peer[idx >> slice_bits] + ((size_t) sp.rank << slice_bits) +
+                                (idx & ((1u << slice_bits) - 1u));
+                *reinterpret_cast<V *>(dst) = x;
+            } else {
+                *reinterpret_cast<V *>(out + base + ((size_t) r << p.s0)) = x;
+            }
         }
     }
 }
@@ -511,7 +532,7 @@ void multi_release(nttb200_plan *p) {
 
 template <int K, int VC, bool CT>
 static int launch_column(nttb200_plan *p, const int32_t *in, int32_t *out, size_t batch, int s0,
-                         cudaStream_t st) {
+                         cudaStream_t st, const ScatterParams *scatter = nullptr) {
     ColParams cp;
     cp.logn = p->logn;
     cp.s0 = (uint32_t) s0;
@@ -521,8 +542,16 @@ static int launch_column(nttb200_plan *p, const int32_t *in, int32_t *out, size_
     uint64_t blocks = (cp.threads + 255) / 256;
     uint64_t cap = (uint64_t) p->sm_count * 64;
     int grid = (int) (blocks < cap ? blocks : cap);
-    column_kernel<K, VC, CT><<<grid, 256, 0, st>>>(reinterpret_cast<const uint32_t *>(in),
-                                                   reinterpret_cast<uint32_t *>(out), p->d_tw, cp);
+    if (scatter) {
+        column_kernel<K, VC, CT, true><<<grid, 256, 0, st>>>(reinterpret_cast<const uint32_t *>(in),
+                                                             reinterpret_cast<uint32_t *>(out),
+                                                             p->d_tw, cp, *scatter);
+    } else {
+        ScatterParams none{};
+        column_kernel<K, VC, CT, false><<<grid, 256, 0, st>>>(reinterpret_cast<const uint32_t *>(in),
+                                                              reinterpret_cast<uint32_t *>(out),
+                                                              p->d_tw, cp, none);
+    }
     g_launches.fetch_add(1, std::memory_order_relaxed);
     NTTB200_CUDA(cudaGetLastError());
     return NTTB200_OK;
@@ -531,16 +560,16 @@ static int launch_column(nttb200_plan *p, const int32_t *in, int32_t *out, size_
 // stages [s0, s0+k) as one column pass; needs s0 >= 2 (128-bit columns) and aligned buffers
 template <bool CT>
 static int column_pass_t(nttb200_plan *p, const int32_t *in, int32_t *out, size_t batch, int s0,
-                         int k, cudaStream_t st) {
+                         int k, cudaStream_t st, const ScatterParams *sc = nullptr) {
     if (s0 < 2 || k < 1 || k > 6 || s0 + k > (int) p->logn) return NTTB200_ERR_UNSUPPORTED;
     if (((uintptr_t) in & 15u) || ((uintptr_t) out & 15u)) return NTTB200_ERR_UNSUPPORTED;
     switch (k) {
-        case 1: return launch_column<1, 4, CT>(p, in, out, batch, s0, st);
-        case 2: return launch_column<2, 4, CT>(p, in, out, batch, s0, st);
-        case 3: return launch_column<3, 4, CT>(p, in, out, batch, s0, st);
-        case 4: return launch_column<4, 4, CT>(p, in, out, batch, s0, st);
-        case 5: return launch_column<5, 2, CT>(p, in, out, batch, s0, st);
-        default: return launch_column<6, 1, CT>(p, in, out, batch, s0, st);
+        case 1: return launch_column<1, 4, CT>(p, in, out, batch, s0, st, sc);
+        case 2: return launch_column<2, 4, CT>(p, in, out, batch, s0, st, sc);
+        case 3: return launch_column<3, 4, CT>(p, in, out, batch, s0, st, sc);
+        case 4: return launch_column<4, 4, CT>(p, in, out, batch, s0, st, sc);
+        case 5: return launch_column<5, 2, CT>(p, in, out, batch, s0, st, sc);
+        default: return launch_column<6, 1, CT>(p, in, out, batch, s0, st, sc);
     }
 }
 
@@ -640,6 +669,61 @@ int launch_multi_gs(nttb200_plan *p, const int32_t *d_in, int32_t *d_out, size_t
         if (rc != NTTB200_OK) return rc;
     }
     p->last_path = "tile_tma + column_passes";
+    return NTTB200_OK;
+}
+
+// Stages [sb, se) of ONE length-N vector (batch 1) with the result scattered to the
+// peers that own it after the transpose (see ScatterParams).  The first stages run
+// as the usual passes in place on d_buf; the last column pass stores remotely.
+// Needs se == logn, a last pass at least log_g stages deep, and slices of >= 4 words.
+int launch_gs_range_scatter(nttb200_plan *p, int32_t *d_buf, int sb, int se, void *const *peers,
+                            int world, int rank, cudaStream_t st) {
+    int log_g = 0;
+    while ((1 << log_g) < world) log_g++;
+    if ((1 << log_g) != world || world > 16 || world < 2 || rank < 0 || rank >= world) {
+        return NTTB200_ERR_INVALID_ARG;
+    }
+    if (se != (int) p->logn || sb < 0 || sb >= se || (int) p->logn - log_g < 2) {
+        return NTTB200_ERR_UNSUPPORTED;
+    }
+    if ((uintptr_t) d_buf & 15u) return NTTB200_ERR_UNSUPPORTED;
+    for (int k = 0; k < world; k++) {
+        if (!peers[k] || ((uintptr_t) peers[k] & 15u)) return NTTB200_ERR_INVALID_ARG;
+    }
+    int s0 = sb;
+    if (sb == 0) {
+        if (!p->d_tw_tile || p->logn < 13) return NTTB200_ERR_UNSUPPORTED;
+        const uint64_t tiles = p->n >> 12;
+        CUtensorMap map_lo, map_hi;
+        if (tile_maps(&map_lo, &map_hi, d_buf, (size_t) tiles) != NTTB200_OK) {
+            return NTTB200_ERR_UNSUPPORTED;
+        }
+        TileParams tp = tile_params(p, d_buf, 1);
+        tile_gs_kernel<false><<<tile_grid(p, tiles), kM_Threads, kM_SmemBytes, st>>>(
+            map_lo, map_hi, map_lo, map_hi, tp);
+        g_launches.fetch_add(1, std::memory_order_relaxed);
+        NTTB200_CUDA(cudaGetLastError());
+        s0 = 12;
+    } else if (sb < 2) {
+        return NTTB200_ERR_UNSUPPORTED;
+    }
+    int rest = se - s0;
+    int passes = (rest + 5) / 6;
+    if (passes < 1) return NTTB200_ERR_UNSUPPORTED;
+    ScatterParams sc{};
+    for (int k = 0; k < world; k++) sc.peer[k] = reinterpret_cast<uint32_t *>(peers[k]);
+    sc.log_g = (uint32_t) log_g;
+    sc.rank = (uint32_t) rank;
+    for (int k = 0; k < passes; k++) {
+        int take = (rest + (passes - k) - 1) / (passes - k);
+        const bool last = k == passes - 1;
+        if (last && take < log_g) return NTTB200_ERR_UNSUPPORTED;  // cannot happen for world <= 16
+        int rc = column_pass_t<false>(p, d_buf, d_buf, 1, s0, take, st, last ? &sc : nullptr);
+        if (rc != NTTB200_OK) return rc;
+        s0 += take;
+        rest -= take;
+    }
+    p->last_path = "passes + peer scatter";
     return NTTB200_OK;
 }
 

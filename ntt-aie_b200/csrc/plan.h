@@ -92,6 +92,8 @@ int launch_multi_gs(nttb200_plan *p, const int32_t *d_in, int32_t *d_out, size_t
                     cudaStream_t st);
 int launch_column_pass(nttb200_plan *p, const int32_t *in, int32_t *out, size_t batch, int s0, int k,
                        cudaStream_t st);
+int launch_gs_range_scatter(nttb200_plan *p, int32_t *d_buf, int sb, int se, void *const *peers,
+                            int world, int rank, cudaStream_t st);
 int launch_multi_ct(nttb200_plan *p, const int32_t *d_in, int32_t *d_out, size_t batch,
                     cudaStream_t st);
 int launch_multi_gs_dual(nttb200_plan *p, const int32_t *d_a, const int32_t *d_b, int32_t *d_out,

@@ -29,6 +29,14 @@ Because the per-stage twiddles are taken from the caller's table by the golden's
 index rule (src/test.cpp:45), the result is bit-exact against the golden ntt() for ANY
 table, not only DFT-valid ones.
 
+Fused exchange (`fused=True`, CUDA engine only).  NCCL's all-to-all costs a launch and a
+protocol round trip that dominate at 8 GPUs (28 MiB per rank).  With the receive
+buffers in symmetric memory (torch.distributed._symmetric_memory: every rank maps every
+peer's buffer) the LAST local pass stores each result straight into the peer that owns
+it after the transpose (`nttb200_gs_stage_range_scatter`), so the transpose rides on the
+pass's own NVLink stores and overlaps its math; the natural-order return trip is fused
+into the cross-GPU pass the same way.  Only two tiny signal barriers remain.
+
 Nothing here computes on the host: the local work goes through an *engine* -- the
 CUDA plans of this package by default.  Tests inject a CPU engine to exercise the
 sharding logic over gloo.
@@ -85,11 +93,31 @@ class CudaEngine:
         self.plan_cross.close()
 
 
+class SymmetricBuffers:
+    """Receive buffers every rank can store into (NVLink peer mappings)."""
+
+    def __init__(self, shard_len: int, device: int, group):
+        import torch
+        import torch.distributed as dist
+        import torch.distributed._symmetric_memory as symm_mem
+        grp = group if group is not None else dist.group.WORLD
+        dev = torch.device("cuda", device)
+        self.scratch = symm_mem.empty(shard_len, dtype=torch.int32, device=dev)
+        self.final = symm_mem.empty(shard_len, dtype=torch.int32, device=dev)
+        self.h_scratch = symm_mem.rendezvous(self.scratch, grp)
+        self.h_final = symm_mem.rendezvous(self.final, grp)
+        self.scratch_ptrs = [int(p) for p in self.h_scratch.buffer_ptrs]
+        self.final_ptrs = [int(p) for p in self.h_final.buffer_ptrs]
+
+    def barrier(self) -> None:
+        self.h_scratch.barrier(channel=0)
+
+
 class FourStepNTT:
     """Golden GS network of length N = 2^logn over `world` ranks (power of two)."""
 
     def __init__(self, logn: int, q: int, table: np.ndarray, rank: int, world: int,
-                 device: Optional[int] = None, engine=None, group=None):
+                 device: Optional[int] = None, engine=None, group=None, fused: bool = False):
         if world & (world - 1) or world < 1:
             raise ValueError("world size must be a power of two")
         self.logn, self.q, self.rank, self.world, self.group = logn, q, rank, world, group
@@ -105,6 +133,13 @@ class FourStepNTT:
         self.t_cross = cross_table(table, world, self.shard)
         self.engine = engine if engine is not None else CudaEngine(
             self.logs, q, self.t_local, self.t_cross, 0 if device is None else device)
+        self.symm = None
+        if fused and world > 1:
+            if engine is not None:
+                raise ValueError("the fused exchange needs the CUDA engine")
+            if self.logs < 13:
+                raise ValueError("fused exchange needs shards of at least 2^13 coefficients")
+            self.symm = SymmetricBuffers(self.shard, 0 if device is None else device, group)
 
     def close(self) -> None:
         if hasattr(self.engine, "close"):
@@ -116,6 +151,8 @@ class FourStepNTT:
         (one of the two buffers)."""
         import torch.distributed as dist
         eng, world = self.engine, self.world
+        if self.symm is not None:
+            return self._forward_fused(shard, natural_order)
         eng.local_full(shard)                                   # step 1
         if world == 1:
             return shard
@@ -126,3 +163,20 @@ class FourStepNTT:
             return scratch
         dist.all_to_all_single(shard, scratch, group=self.group)  # step 4
         return shard
+
+    def _forward_fused(self, shard, natural_order: bool):
+        """Steps 1-4 with both transposes fused into the passes' stores.  Returns the
+        symmetric buffer that holds the result (valid until the next call)."""
+        eng, sy = self.engine, self.symm
+        logc = self.logs - (self.world.bit_length() - 1)
+        # steps 1+2: local stages; the last pass scatters into every rank's scratch
+        eng.plan_local.gs_stage_range_scatter(shard, 0, self.logs, sy.scratch_ptrs, self.rank)
+        sy.barrier()                      # all slices have landed everywhere
+        if not natural_order:
+            eng.plan_cross.gs_stage_range(sy.scratch, sy.scratch, 1, logc, self.logs)   # step 3
+            sy.barrier()                  # peers may overwrite scratch only after this
+            return sy.scratch
+        # steps 3+4: cross-GPU stages; their results go straight home
+        eng.plan_cross.gs_stage_range_scatter(sy.scratch, logc, self.logs, sy.final_ptrs, self.rank)
+        sy.barrier()
+        return sy.final

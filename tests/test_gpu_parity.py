@@ -287,7 +287,10 @@ def test_fourstep_on_available_gpus(lib):
     import sys
     root = os.path.dirname(os.path.dirname(os.path.dirname(lib.lib_path())))
     world = min(2, torch.cuda.device_count())
-    for extra in ([], ["--arbitrary-table"]):
+    variants = [[], ["--arbitrary-table"]]
+    if world > 1:
+        variants.append(["--fused", "--arbitrary-table"])   # transposes fused into peer stores
+    for extra in variants:
         cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1",
                f"--nproc-per-node={world}", "--master-addr", "127.0.0.1", "--master-port", "29533",
                os.path.join(root, "tools", "fourstep_run.py"), "--logn", "18", "--verify",

@@ -32,6 +32,8 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=2)
     ap.add_argument("--verify", action="store_true")
+    ap.add_argument("--fused", action="store_true",
+                    help="transposes fused into the passes' NVLink stores (symmetric memory)")
     ap.add_argument("--arbitrary-table", action="store_true",
                     help="random table instead of the reference's w^i (table-driven check)")
     args = ap.parse_args()
@@ -56,7 +58,7 @@ def main():
     t_table = time.perf_counter() - t0
     rng = np.random.default_rng(0x5EED0026)
     a = rng.integers(0, Q, n, dtype=np.int32)            # same vector on every rank (seeded)
-    plan = FourStepNTT(args.logn, Q, table, rank, world, device=local)
+    plan = FourStepNTT(args.logn, Q, table, rank, world, device=local, fused=args.fused)
     shard0 = torch.from_numpy(a[rank * s:(rank + 1) * s].copy()).cuda()
     shard = torch.empty_like(shard0)
     scratch = torch.empty_like(shard0)
@@ -91,7 +93,9 @@ def main():
 
     # the all-to-all alone (same buffers), for the NVLink roofline
     a2a_ms = None
-    if world > 1:
+    if world > 1 and not args.fused:
+        for _ in range(2):
+            dist.all_to_all_single(scratch, shard)
         sync()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
@@ -106,7 +110,7 @@ def main():
     ok = None
     if args.verify:
         shard.copy_(shard0)
-        res = plan.forward(shard, scratch, natural_order=True)
+        res = plan.forward(shard, scratch, natural_order=True).clone()
         parts = [torch.empty_like(res) for _ in range(world)] if rank == 0 else None
         if world > 1:
             dist.gather(res, parts, dst=0)
@@ -125,6 +129,7 @@ def main():
         line = {
             "workload": f"single four-step NTT N=2^{args.logn}, q={Q}, {world} GPU(s)",
             "n_gpus": world, "logn": args.logn,
+            "exchange": "fused peer stores (symmetric memory)" if args.fused else "NCCL all_to_all_single",
             "ms_transposed_order": ms_dev, "ms_natural_order": ms_nat,
             "butterflies_per_s_transposed": bfly / (ms_dev * 1e-3),
             "butterflies_per_s_natural": bfly / (ms_nat * 1e-3),

@@ -21,6 +21,10 @@ for n in 2 4 8; do
   [ $n -le $G ] || continue
   run_tr $n tools/fourstep_run.py --logn 26 --verify --steps 5 2>/dev/null | grep '^{' >> gpurun_out/multigpu_fourstep.jsonl
 done
+for n in 2 4 8; do
+  [ $n -le $G ] || continue
+  run_tr $n tools/fourstep_run.py --logn 26 --verify --steps 5 --fused 2>/dev/null | grep '^{' >> gpurun_out/multigpu_fourstep.jsonl
+done
 python - <<'PY'
 import json
 for f in ("gpurun_out/multigpu_bench.jsonl", "gpurun_out/multigpu_fourstep.jsonl"):
@@ -30,6 +34,6 @@ for f in ("gpurun_out/multigpu_bench.jsonl", "gpurun_out/multigpu_fourstep.jsonl
             print("bench n_gpus", d["n_gpus"], "polys/s %.4g" % d["value"], "ms/step %.4f" % d["ms_per_step"],
                   "e2e %.4g" % (d["e2e"]["value"] or 0), "clocks", d["clocks"]["sm_mhz"], d["clocks"]["reasons"])
         else:
-            print("fourstep n_gpus", d["n_gpus"], "ms dev-order %.3f nat %.3f" % (d["ms_transposed_order"], d["ms_natural_order"]),
+            print("fourstep", d.get("exchange", "")[:5], "n_gpus", d["n_gpus"], "ms dev-order %.3f nat %.3f" % (d["ms_transposed_order"], d["ms_natural_order"]),
                   "a2a ms", d["all_to_all_ms"], "GB/s/dir", d["all_to_all_GBps_per_gpu_per_dir"], "exact", d["bit_exact_vs_golden"])
 PY
