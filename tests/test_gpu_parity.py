@@ -360,3 +360,27 @@ def test_small_n_warp_kernel_ragged_batches(lib, oracle_mod, logn):
         out, path = run_gs(lib, a, g["roots"], 3329, flags=1)
         assert "small" in path
         assert np.array_equal(out, oracle_mod.ans_order_permute(oracle_mod.ntt_gs(a, g["roots"], 3329)))
+
+
+@pytest.mark.parametrize("logn", [10, 12, 14])
+def test_extreme_moduli_on_fast_paths(lib, oracle_mod, logn):
+    """q = 2^30 (the largest modulus of the golden's domain, where the lazy ranges
+    [0,2q) / [0,4q) touch 2^32), q = 2 and q = 3 through the register-radix kernels,
+    GS and CT, inputs pinned at q-1."""
+    n = 1 << logn
+    rng = np.random.default_rng(12000 + logn)
+    for q in (1 << 30, (1 << 30) - 35, 2, 3):
+        table = rng.integers(0, q, n, dtype=np.int32)
+        a = rng.integers(0, q, (4, n), dtype=np.int32)
+        a[0] = q - 1
+        table[1::2] = q - 1
+        out, path = run_gs(lib, a, table, q)
+        assert path != "generic_stage_pass" or logn < 9
+        assert np.array_equal(out, oracle_mod.ntt_gs(a, table, q)), (logn, q, path)
+        if logn >= 12:
+            d_in = dev(a)
+            d_out = torch.empty_like(d_in)
+            with lib.Plan(logn, q, table) as plan:
+                plan.ct(d_in, d_out, 4)
+                assert "ct" in plan.last_path
+            assert np.array_equal(d_out.cpu().numpy(), oracle_mod.ntt_ct(a, table, q)), (logn, q)
