@@ -198,7 +198,6 @@ int nttb200_plan_destroy(nttb200_plan *p) {
         for (int k = 0; k < kHostStreams; k++) {
             if (p->hstream[k]) cudaStreamSynchronize(p->hstream[k]);
             if (p->d_stage[k]) cudaFree(p->d_stage[k]);
-            if (p->hevent[k]) cudaEventDestroy(p->hevent[k]);
             if (p->hstream[k]) cudaStreamDestroy(p->hstream[k]);
         }
     }
@@ -320,7 +319,6 @@ static int host_prepare(nttb200_plan *p) {
     if (polys < 1) polys = 1;
     for (int k = 0; k < kHostStreams; k++) {
         NTTB200_CUDA(cudaStreamCreateWithFlags(&p->hstream[k], cudaStreamNonBlocking));
-        NTTB200_CUDA(cudaEventCreateWithFlags(&p->hevent[k], cudaEventDisableTiming));
         NTTB200_CUDA(cudaMalloc(&p->d_stage[k], sizeof(int32_t) * polys * p->n));
     }
     p->stage_polys = polys;

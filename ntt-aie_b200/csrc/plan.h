@@ -43,7 +43,6 @@ struct nttb200_plan {
     // nttb200_gs_host resources (lazily created, guarded by host_mu)
     std::mutex host_mu;
     cudaStream_t hstream[nttb200::kHostStreams] = {};
-    cudaEvent_t hevent[nttb200::kHostStreams] = {};
     int32_t *d_stage[nttb200::kHostStreams] = {};
     size_t stage_polys = 0;  // capacity of each staging buffer in polynomials
     bool host_ready = false;
