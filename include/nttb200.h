@@ -161,6 +161,29 @@ NTTB200_API int nttb200_polymul_negacyclic(nttb200_plan *fwd, nttb200_plan *inv,
                                            const int32_t *d_a, const int32_t *d_b, int32_t *d_c,
                                            size_t batch, void *cuda_stream);
 
+/* ---- RNS batches (new) ------------------------------------------- */
+
+/* Polynomials in residue-number-system form: L channels ("limbs") modulo L different
+ * primes, N = 4096, coefficients laid out [batch][L][4096]; channel l is transformed
+ * modulo q[l] with its own table tables_host[l] (4096 words, the golden's table[h+i]
+ * rule).  One launch serves all channels: the kernels pick twiddles AND modulus by
+ * channel.  1 <= L <= 32. */
+typedef struct nttb200_rns_plan nttb200_rns_plan;
+NTTB200_API int nttb200_rns_plan_create(nttb200_rns_plan **plan, int device, uint32_t limbs,
+                                        const uint32_t *q, const int32_t *const *tables_host,
+                                        uint32_t flags);
+NTTB200_API int nttb200_rns_plan_destroy(nttb200_rns_plan *plan);
+/* golden GS network / CT network on every channel of every polynomial */
+NTTB200_API int nttb200_rns_gs_batch(nttb200_rns_plan *plan, const int32_t *d_in, int32_t *d_out,
+                                     size_t batch, void *cuda_stream);
+NTTB200_API int nttb200_rns_ct_batch(nttb200_rns_plan *plan, const int32_t *d_in, int32_t *d_out,
+                                     size_t batch, void *cuda_stream);
+/* c = a (*) b mod (x^4096 + 1, q[l]) on every channel; fwd holds psi_l^bitrev tables,
+ * inv psi_l^-bitrev tables of the same primes */
+NTTB200_API int nttb200_rns_polymul_negacyclic(nttb200_rns_plan *fwd, nttb200_rns_plan *inv,
+                                               const int32_t *d_a, const int32_t *d_b, int32_t *d_c,
+                                               size_t batch, void *cuda_stream);
+
 /* ---- introspection ---------------------------------------------------------- */
 NTTB200_API const char *nttb200_strerror(int status);
 /* text of the last CUDA error seen by the calling thread ("" if none) */

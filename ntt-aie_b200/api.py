@@ -62,6 +62,12 @@ def load_library():
         "nttb200_pointwise": (ctypes.c_int, [vp, vp, vp, vp, sz, vp]),
         "nttb200_scale": (ctypes.c_int, [vp, vp, vp, sz, i32, vp]),
         "nttb200_polymul_negacyclic": (ctypes.c_int, [vp, vp, vp, vp, vp, sz, vp]),
+        "nttb200_rns_plan_create": (ctypes.c_int, [ctypes.POINTER(vp), ctypes.c_int, u32,
+                                                   ctypes.POINTER(u32), ctypes.POINTER(_i32p), u32]),
+        "nttb200_rns_plan_destroy": (ctypes.c_int, [vp]),
+        "nttb200_rns_gs_batch": (ctypes.c_int, [vp, vp, vp, sz, vp]),
+        "nttb200_rns_ct_batch": (ctypes.c_int, [vp, vp, vp, sz, vp]),
+        "nttb200_rns_polymul_negacyclic": (ctypes.c_int, [vp, vp, vp, vp, vp, sz, vp]),
         "nttb200_strerror": (ctypes.c_char_p, [ctypes.c_int]),
         "nttb200_last_error": (ctypes.c_char_p, []),
         "nttb200_kernel_launches": (ctypes.c_uint64, []),
@@ -82,6 +88,8 @@ EXPORTED_SYMBOLS = (
     "nttb200_make_roots", "nttb200_make_bitrev_table", "nttb200_powmod", "nttb200_plan_create",
     "nttb200_plan_destroy", "nttb200_gs_batch", "nttb200_ct_batch", "nttb200_gs_stage_range",
     "nttb200_gs_host", "nttb200_gs_stage_range_scatter", "nttb200_pointwise", "nttb200_scale", "nttb200_polymul_negacyclic",
+    "nttb200_rns_plan_create", "nttb200_rns_plan_destroy", "nttb200_rns_gs_batch",
+    "nttb200_rns_ct_batch", "nttb200_rns_polymul_negacyclic",
     "nttb200_strerror", "nttb200_last_error", "nttb200_kernel_launches", "nttb200_plan_last_path",
     "nttb200_plan_logn", "nttb200_plan_modulus", "nttb200_version",
 )
@@ -224,6 +232,56 @@ class Plan:
     def scale(self, d_a, d_c, count: int, scalar: int, stream=None) -> None:
         _check(self._lib.nttb200_scale(self._h, _addr(d_a), _addr(d_c), count, scalar,
                                        _stream(stream)), "scale")
+
+
+class RnsPlan:
+    """N = 4096 polynomials in RNS form: L channels with their own primes and tables,
+    data laid out [batch][L][4096]; one launch per transform serves all channels."""
+
+    def __init__(self, qs, tables, device: int = 0):
+        self._lib = load_library()
+        self.limbs = len(qs)
+        tabs = [np.ascontiguousarray(t, dtype=np.int32) for t in tables]
+        if len(tabs) != self.limbs or any(t.size != 4096 for t in tabs):
+            raise ValueError("one 4096-word table per modulus")
+        qarr = (ctypes.c_uint32 * self.limbs)(*[int(q) for q in qs])
+        parr = (_i32p * self.limbs)(*[t.ctypes.data_as(_i32p) for t in tabs])
+        handle = ctypes.c_void_p()
+        _check(self._lib.nttb200_rns_plan_create(ctypes.byref(handle), device, self.limbs, qarr, parr,
+                                                 0), "rns_plan_create")
+        self._h = handle
+        self.qs = [int(q) for q in qs]
+
+    def close(self) -> None:
+        if getattr(self, "_h", None):
+            self._lib.nttb200_rns_plan_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+
+    def gs(self, d_in, d_out, batch: int, stream=None) -> None:
+        _check(self._lib.nttb200_rns_gs_batch(self._h, _addr(d_in), _addr(d_out), batch,
+                                              _stream(stream)), "rns_gs_batch")
+
+    def ct(self, d_in, d_out, batch: int, stream=None) -> None:
+        _check(self._lib.nttb200_rns_ct_batch(self._h, _addr(d_in), _addr(d_out), batch,
+                                              _stream(stream)), "rns_ct_batch")
+
+
+def rns_polymul_negacyclic(fwd: RnsPlan, inv: RnsPlan, d_a, d_b, d_c, batch: int, stream=None) -> None:
+    _check(fwd._lib.nttb200_rns_polymul_negacyclic(fwd._h, inv._h, _addr(d_a), _addr(d_b),
+                                                   _addr(d_c), batch, _stream(stream)),
+           "rns_polymul_negacyclic")
 
 
 def polymul_negacyclic(fwd: Plan, inv: Plan, d_a, d_b, d_c, batch: int, stream=None) -> None:

@@ -415,6 +415,104 @@ int nttb200_polymul_negacyclic(nttb200_plan *fwd, nttb200_plan *inv, const int32
     return rc;
 }
 
+/* --------------------------------------------------------------------- RNS */
+int nttb200_rns_plan_create(nttb200_rns_plan **out, int device, uint32_t limbs, const uint32_t *q,
+                            const int32_t *const *tables_host, uint32_t flags) {
+    if (!out) return NTTB200_ERR_INVALID_ARG;
+    *out = nullptr;
+    if (!q || !tables_host || limbs < 1 || limbs > 32 || flags != 0) return NTTB200_ERR_INVALID_ARG;
+    nttb200_rns_plan *rp = new (std::nothrow) nttb200_rns_plan();
+    if (!rp) return NTTB200_ERR_ALLOC;
+    rp->device = device;
+    rp->limbs = limbs;
+    int rc = NTTB200_OK;
+    for (uint32_t l = 0; l < limbs && rc == NTTB200_OK; l++) {
+        nttb200_plan *sp = nullptr;
+        rc = nttb200_plan_create(&sp, device, 12, q[l], tables_host[l], 0);
+        if (rc == NTTB200_OK) {
+            rp->sub.push_back(sp);
+            if (!sp->d_tw_tile) rc = NTTB200_ERR_UNSUPPORTED;
+        }
+    }
+    if (rc == NTTB200_OK) {
+        DeviceGuard guard(device);
+        rp->sm_count = rp->sub[0]->sm_count;
+        cudaError_t e = cudaMalloc(&rp->d_tw_tile, sizeof(uint4) * kRnsTwTile * limbs);
+        if (e != cudaSuccess) rc = cuda_fail(e, "cudaMalloc(rns tables)");
+        for (uint32_t l = 0; l < limbs && rc == NTTB200_OK; l++) {
+            e = cudaMemcpy(rp->d_tw_tile + (size_t) l * kRnsTwTile, rp->sub[l]->d_tw_tile,
+                           sizeof(uint4) * kRnsTwTile, cudaMemcpyDeviceToDevice);
+            if (e != cudaSuccess) rc = cuda_fail(e, "cudaMemcpy(rns tables)");
+            const nttb200_plan *sp = rp->sub[l];
+            uint4 pc = make_uint4(sp->q, 0, 0, 0);
+            if (sp->q & 1u) {
+                pc.y = rns_inv_mod_2_32(sp->q);
+                uint64_t sc = ((uint64_t) sp->n_inv << 32) % sp->q;
+                pc.z = (uint32_t) sc;
+                pc.w = (uint32_t) ((sc << 32) / sp->q);
+            }
+            rp->pos.push_back(pc);
+        }
+    }
+    if (rc != NTTB200_OK) {
+        nttb200_rns_plan_destroy(rp);
+        return rc;
+    }
+    *out = rp;
+    return NTTB200_OK;
+}
+
+int nttb200_rns_plan_destroy(nttb200_rns_plan *rp) {
+    if (!rp) return NTTB200_OK;
+    {
+        DeviceGuard guard(rp->device);
+        if (rp->d_tw_tile) cudaFree(rp->d_tw_tile);
+    }
+    for (nttb200_plan *sp : rp->sub) nttb200_plan_destroy(sp);
+    delete rp;
+    return NTTB200_OK;
+}
+
+static int rns_run(nttb200_rns_plan *rp, int kind, const int32_t *d_a, const int32_t *d_b,
+                   int32_t *d_out, size_t batch, void *stream) {
+    if (!rp || (batch && (!d_a || !d_out))) return NTTB200_ERR_INVALID_ARG;
+    DeviceGuard guard(rp->device);
+    return rns_launch(rp->sm_count, kind, rp->d_tw_tile, rp->pos.data(), rp->limbs, d_a, d_b, d_out,
+                      batch, (cudaStream_t) stream);
+}
+
+int nttb200_rns_gs_batch(nttb200_rns_plan *rp, const int32_t *d_in, int32_t *d_out, size_t batch,
+                         void *stream) {
+    return rns_run(rp, 0, d_in, nullptr, d_out, batch, stream);
+}
+
+int nttb200_rns_ct_batch(nttb200_rns_plan *rp, const int32_t *d_in, int32_t *d_out, size_t batch,
+                         void *stream) {
+    return rns_run(rp, 1, d_in, nullptr, d_out, batch, stream);
+}
+
+int nttb200_rns_polymul_negacyclic(nttb200_rns_plan *fwd, nttb200_rns_plan *inv, const int32_t *d_a,
+                                   const int32_t *d_b, int32_t *d_c, size_t batch, void *stream) {
+    if (!fwd || !inv || (batch && (!d_a || !d_b || !d_c))) return NTTB200_ERR_INVALID_ARG;
+    if (fwd->limbs != inv->limbs || fwd->device != inv->device) return NTTB200_ERR_INVALID_ARG;
+    for (uint32_t l = 0; l < fwd->limbs; l++) {
+        if (fwd->pos[l].x != inv->pos[l].x) return NTTB200_ERR_INVALID_ARG;
+        if (!(fwd->pos[l].x & 1u)) return NTTB200_ERR_MODULUS;
+    }
+    if (batch == 0) return NTTB200_OK;
+    DeviceGuard guard(fwd->device);
+    cudaStream_t st = (cudaStream_t) stream;
+    const size_t words = batch * fwd->limbs * 4096;
+    int32_t *tmp = nullptr;
+    NTTB200_CUDA(cudaMallocAsync(&tmp, sizeof(int32_t) * words * 2, st));
+    int rc = rns_run(fwd, 1, d_a, nullptr, tmp, batch, stream);
+    if (rc == NTTB200_OK) rc = rns_run(fwd, 1, d_b, nullptr, tmp + words, batch, stream);
+    if (rc == NTTB200_OK) rc = rns_run(inv, 2, tmp, tmp + words, d_c, batch, stream);
+    cudaError_t e = cudaFreeAsync(tmp, st);
+    if (rc == NTTB200_OK && e != cudaSuccess) rc = cuda_fail(e, "cudaFreeAsync");
+    return rc;
+}
+
 /* ---------------------------------------------------------- introspection */
 const char *nttb200_strerror(int status) {
     switch (status) {

@@ -121,17 +121,27 @@ struct TileParams {
     uint32_t scale_shoup;
 };
 
+// RNS: tile position c = residue-channel index, each with its own modulus:
+// pos[c] = (q_c, q_c^-1 mod 2^32, scale_c, scale_c's Shoup companion).  Passed as a kernel
+// parameter so that the (warp-uniform) lookup is a uniform constant-bank load and the
+// modulus stays in uniform registers, as in the single-modulus kernels.
+constexpr int kM_MaxChannels = 32;
+struct RnsConsts {
+    uint4 pos[kM_MaxChannels];
+};
+
 // DUAL = false: plain golden stages 0..11 of every tile.
 // DUAL = true : the tile's input is the pointwise product of two buffers (second pair
 //   of tensor maps), taken as a Montgomery product a*b*2^-32, and every output is
 //   multiplied by `scale` (= N^-1 * 2^32 mod q for the inverse transform of a
 //   negacyclic product).  The network is linear, so scaling here instead of after the
 //   last column pass gives the same residues.
-template <bool DUAL>
+template <bool DUAL, bool RNS>
 __global__ void __launch_bounds__(kM_Threads, 1)
 tile_gs_kernel(const __grid_constant__ CUtensorMap map_lo, const __grid_constant__ CUtensorMap map_hi,
                const __grid_constant__ CUtensorMap map_b_lo,
-               const __grid_constant__ CUtensorMap map_b_hi, const TileParams prm) {
+               const __grid_constant__ CUtensorMap map_b_hi, const TileParams prm,
+               const __grid_constant__ RnsConsts rns) {
     extern __shared__ uint8_t smem_raw[];
     const uint32_t data_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
     const uint32_t bar_base = data_base + kM_Teams * kF_PolyBytes;
@@ -141,7 +151,9 @@ tile_gs_kernel(const __grid_constant__ CUtensorMap map_lo, const __grid_constant
     // registers instead of taking a third vector-register read port in every IADD3
     const int team = __shfl_sync(0xffffffffu, tid >> 6, 0);
     const int j = tid & 63;
-    const uint32_t q = prm.q, two_q = 2u * prm.q, zero = prm.zero;
+    uint32_t q = prm.q, two_q = 2u * prm.q;
+    uint32_t qinv = prm.qinv, scale = prm.scale, scale_shoup = prm.scale_shoup;
+    const uint32_t zero = prm.zero;
 
     if (tid < kM_Teams) mbar_init(bar_base + tid * 8, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -181,6 +193,14 @@ tile_gs_kernel(const __grid_constant__ CUtensorMap map_lo, const __grid_constant
     for (; u < u_end; u += kM_Teams) {
         uint32_t v[64];
         const uint4 *tw = prm.tw_tile + (size_t) c_cur * kM_TwTile;
+        if (RNS) {
+            const uint4 pc = rns.pos[c_cur];
+            q = pc.x;
+            two_q = 2u * pc.x;
+            qinv = pc.y;
+            scale = pc.z;
+            scale_shoup = pc.w;
+        }
         mbar_wait(bar, parity);
         parity ^= 1;
 #pragma unroll
@@ -208,7 +228,7 @@ tile_gs_kernel(const __grid_constant__ CUtensorMap map_lo, const __grid_constant
 #pragma unroll
                 for (int e = 0; e < 4; e++) {
                     uint64_t prod = (uint64_t) v[4 * c + e] * bb[e];
-                    uint32_t m = (uint32_t) prod * prm.qinv;
+                    uint32_t m = (uint32_t) prod * qinv;
                     v[4 * c + e] = (uint32_t) (prod >> 32) - __umulhi(m, q) + q;
                 }
             }
@@ -254,7 +274,7 @@ tile_gs_kernel(const __grid_constant__ CUtensorMap map_lo, const __grid_constant
         uint32_t *dst = prm.out + (size_t) tile_store * 4096 + j;
 #pragma unroll
         for (int i = 0; i < 64; i++) {
-            uint32_t r = DUAL ? shoup_mul_lazy(v[i], prm.scale, prm.scale_shoup, q) : v[i];
+            uint32_t r = DUAL ? shoup_mul_lazy(v[i], scale, scale_shoup, q) : v[i];
             dst[i * 64] = min(r - q, r);
         }
     }
@@ -263,10 +283,11 @@ tile_gs_kernel(const __grid_constant__ CUtensorMap map_lo, const __grid_constant
 // Forward partner: CT stages 11..0 of every tile (stride 2048 -> 1).  Columns first
 // (uniform twiddles), exchange, rows (thread-private twiddles); the rows go back to the
 // team's buffer and leave through a TMA store.
+template <bool RNS>
 __global__ void __launch_bounds__(kM_Threads, 1)
 tile_ct_kernel(const __grid_constant__ CUtensorMap map_lo, const __grid_constant__ CUtensorMap map_hi,
                const __grid_constant__ CUtensorMap out_lo, const __grid_constant__ CUtensorMap out_hi,
-               const TileParams prm) {
+               const TileParams prm, const __grid_constant__ RnsConsts rns) {
     extern __shared__ uint8_t smem_raw[];
     const uint32_t data_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
     const uint32_t bar_base = data_base + kM_Teams * kF_PolyBytes;
@@ -276,7 +297,8 @@ tile_ct_kernel(const __grid_constant__ CUtensorMap map_lo, const __grid_constant
     // registers instead of taking a third vector-register read port in every IADD3
     const int team = __shfl_sync(0xffffffffu, tid >> 6, 0);
     const int j = tid & 63;
-    const uint32_t q = prm.q, two_q = 2u * prm.q, zero = prm.zero;
+    uint32_t q = prm.q, two_q = 2u * prm.q;
+    const uint32_t zero = prm.zero;
 
     if (tid < kM_Teams) mbar_init(bar_base + tid * 8, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -311,6 +333,11 @@ tile_ct_kernel(const __grid_constant__ CUtensorMap map_lo, const __grid_constant
     for (; u < u_end; u += kM_Teams) {
         uint32_t v[64];
         const uint4 *tw = prm.tw_tile + (size_t) c_cur * kM_TwTile;
+        if (RNS) {
+            const uint4 pc = rns.pos[c_cur];
+            q = pc.x;
+            two_q = 2u * pc.x;
+        }
         mbar_wait(bar, parity);
         parity ^= 1;
         // ---- columns: register i = a[j + 64 i]; stages 11..6
@@ -490,6 +517,19 @@ column_kernel(const uint32_t *__restrict__ in, uint32_t *__restrict__ out,
 // --------------------------------------------------------------------- host side
 int tile_maps(CUtensorMap *lo, CUtensorMap *hi, const int32_t *base, size_t tiles);  // kernels_fused.cu
 
+static const RnsConsts kNoRns{};
+
+int multi_set_attrs() {
+    const auto attr = cudaFuncAttributeMaxDynamicSharedMemorySize;
+    NTTB200_CUDA(cudaFuncSetAttribute(tile_gs_kernel<false, false>, attr, kM_SmemBytes));
+    NTTB200_CUDA(cudaFuncSetAttribute(tile_gs_kernel<true, false>, attr, kM_SmemBytes));
+    NTTB200_CUDA(cudaFuncSetAttribute(tile_gs_kernel<false, true>, attr, kM_SmemBytes));
+    NTTB200_CUDA(cudaFuncSetAttribute(tile_gs_kernel<true, true>, attr, kM_SmemBytes));
+    NTTB200_CUDA(cudaFuncSetAttribute(tile_ct_kernel<false>, attr, kM_SmemBytes));
+    NTTB200_CUDA(cudaFuncSetAttribute(tile_ct_kernel<true>, attr, kM_SmemBytes));
+    return NTTB200_OK;
+}
+
 int multi_prepare(nttb200_plan *p) {
     if (p->logn < 12 || p->logn > 26) return NTTB200_ERR_UNSUPPORTED;
     const uint32_t chunks = p->n >> 12;
@@ -516,13 +556,7 @@ int multi_prepare(nttb200_plan *p) {
     }
     NTTB200_CUDA(cudaMalloc(&p->d_tw_tile, sizeof(uint4) * t.size()));
     NTTB200_CUDA(cudaMemcpy(p->d_tw_tile, t.data(), sizeof(uint4) * t.size(), cudaMemcpyHostToDevice));
-    NTTB200_CUDA(cudaFuncSetAttribute(tile_gs_kernel<false>,
-                                      cudaFuncAttributeMaxDynamicSharedMemorySize, kM_SmemBytes));
-    NTTB200_CUDA(cudaFuncSetAttribute(tile_gs_kernel<true>,
-                                      cudaFuncAttributeMaxDynamicSharedMemorySize, kM_SmemBytes));
-    NTTB200_CUDA(cudaFuncSetAttribute(tile_ct_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                      kM_SmemBytes));
-    return NTTB200_OK;
+    return multi_set_attrs();
 }
 
 void multi_release(nttb200_plan *p) {
@@ -621,10 +655,11 @@ static int launch_multi_gs_once(nttb200_plan *p, const int32_t *d_in, const int3
         uint64_t sc = ((uint64_t) p->n_inv << 32) % p->q;
         tp.scale = (uint32_t) sc;
         tp.scale_shoup = (uint32_t) ((sc << 32) / p->q);
-        tile_gs_kernel<true><<<grid, kM_Threads, kM_SmemBytes, st>>>(map_lo, map_hi, b_lo, b_hi, tp);
+        tile_gs_kernel<true, false><<<grid, kM_Threads, kM_SmemBytes, st>>>(map_lo, map_hi, b_lo, b_hi,
+                                                                            tp, kNoRns);
     } else {
-        tile_gs_kernel<false><<<grid, kM_Threads, kM_SmemBytes, st>>>(map_lo, map_hi, map_lo, map_hi,
-                                                                      tp);
+        tile_gs_kernel<false, false><<<grid, kM_Threads, kM_SmemBytes, st>>>(map_lo, map_hi, map_lo,
+                                                                             map_hi, tp, kNoRns);
     }
     g_launches.fetch_add(1, std::memory_order_relaxed);
     NTTB200_CUDA(cudaGetLastError());
@@ -699,8 +734,8 @@ int launch_gs_range_scatter(nttb200_plan *p, int32_t *d_buf, int sb, int se, voi
             return NTTB200_ERR_UNSUPPORTED;
         }
         TileParams tp = tile_params(p, d_buf, 1);
-        tile_gs_kernel<false><<<tile_grid(p, tiles), kM_Threads, kM_SmemBytes, st>>>(
-            map_lo, map_hi, map_lo, map_hi, tp);
+        tile_gs_kernel<false, false><<<tile_grid(p, tiles), kM_Threads, kM_SmemBytes, st>>>(
+            map_lo, map_hi, map_lo, map_hi, tp, kNoRns);
         g_launches.fetch_add(1, std::memory_order_relaxed);
         NTTB200_CUDA(cudaGetLastError());
         s0 = 12;
@@ -772,12 +807,58 @@ int launch_multi_ct(nttb200_plan *p, const int32_t *d_in, int32_t *d_out, size_t
         return NTTB200_ERR_UNSUPPORTED;
     }
     TileParams tp = tile_params(p, d_out, batch);
-    tile_ct_kernel<<<tile_grid(p, tiles), kM_Threads, kM_SmemBytes, st>>>(in_lo, in_hi, out_lo, out_hi,
-                                                                          tp);
+    tile_ct_kernel<false><<<tile_grid(p, tiles), kM_Threads, kM_SmemBytes, st>>>(
+        in_lo, in_hi, out_lo, out_hi, tp, kNoRns);
     g_launches.fetch_add(1, std::memory_order_relaxed);
     NTTB200_CUDA(cudaGetLastError());
     p->last_path = "column_passes_ct + tile_tma_ct";
     return NTTB200_OK;
 }
+
+// ------------------------------------------------------------------------- RNS
+// N = 4096, L residue channels: coefficients [batch][L][4096]; channel l is transformed
+// modulo q_l with its own table.  The tile kernels already pick their twiddles by tile
+// position; here the position is the channel and also selects the modulus.
+int rns_launch(int sm_count, int kind, const uint4 *d_tw_tile, const uint4 *h_pos, uint32_t limbs,
+               const int32_t *d_a, const int32_t *d_b, int32_t *d_out, size_t batch,
+               cudaStream_t st) {
+    const uint64_t tiles = (uint64_t) batch * limbs;
+    if (tiles == 0) return NTTB200_OK;
+    if (limbs > (uint32_t) kM_MaxChannels) return NTTB200_ERR_UNSUPPORTED;
+    if (tiles > 0x7fffffffull || batch > 0xffffffffull || ((uintptr_t) d_a & 15u) ||
+        ((uintptr_t) d_out & 15u) || (d_b && ((uintptr_t) d_b & 15u))) {
+        return NTTB200_ERR_UNSUPPORTED;
+    }
+    RnsConsts rc{};
+    for (uint32_t l = 0; l < limbs; l++) rc.pos[l] = h_pos[l];
+    TileParams tp;
+    tp.out = reinterpret_cast<uint32_t *>(d_out);
+    tp.tw_tile = d_tw_tile;
+    tp.batch = (uint32_t) batch;
+    tp.chunks = limbs;
+    tp.q = 0;
+    tp.zero = 0;
+    tp.qinv = tp.scale = tp.scale_shoup = 0;
+    uint64_t ctas = (tiles + kM_Teams - 1) / kM_Teams;
+    int grid = (int) (ctas < (uint64_t) sm_count ? ctas : (uint64_t) sm_count);
+    CUtensorMap a_lo, a_hi, b_lo, b_hi;
+    if (tile_maps(&a_lo, &a_hi, d_a, (size_t) tiles) != NTTB200_OK) return NTTB200_ERR_CUDA;
+    if (kind == 0) {         // GS
+        tile_gs_kernel<false, true><<<grid, kM_Threads, kM_SmemBytes, st>>>(a_lo, a_hi, a_lo, a_hi, tp,
+                                                                            rc);
+    } else if (kind == 1) {  // CT (output tensor maps on d_out)
+        if (tile_maps(&b_lo, &b_hi, d_out, (size_t) tiles) != NTTB200_OK) return NTTB200_ERR_CUDA;
+        tile_ct_kernel<true><<<grid, kM_Threads, kM_SmemBytes, st>>>(a_lo, a_hi, b_lo, b_hi, tp, rc);
+    } else {                 // GS of the pointwise product, scaled
+        if (tile_maps(&b_lo, &b_hi, d_b, (size_t) tiles) != NTTB200_OK) return NTTB200_ERR_CUDA;
+        tile_gs_kernel<true, true><<<grid, kM_Threads, kM_SmemBytes, st>>>(a_lo, a_hi, b_lo, b_hi, tp,
+                                                                           rc);
+    }
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+    NTTB200_CUDA(cudaGetLastError());
+    return NTTB200_OK;
+}
+
+uint32_t rns_inv_mod_2_32(uint32_t q) { return inv_mod_2_32(q); }
 
 }  // namespace nttb200

@@ -5,6 +5,7 @@
 
 #include <atomic>
 #include <mutex>
+#include <vector>
 
 #include "../../include/nttb200.h"
 
@@ -46,6 +47,16 @@ struct nttb200_plan {
     int32_t *d_stage[nttb200::kHostStreams] = {};
     size_t stage_polys = 0;  // capacity of each staging buffer in polynomials
     bool host_ready = false;
+};
+
+// N = 4096, L residue channels with their own moduli and tables
+struct nttb200_rns_plan {
+    int device = 0;
+    uint32_t limbs = 0;
+    int sm_count = 148;
+    std::vector<nttb200_plan *> sub;   // one validated single-modulus plan per channel
+    uint4 *d_tw_tile = nullptr;        // [limbs][32][65]
+    std::vector<uint4> pos;            // (q, q^-1 mod 2^32, N^-1*2^32 mod q, its Shoup companion)
 };
 
 namespace nttb200 {
@@ -93,6 +104,11 @@ int launch_column_pass(nttb200_plan *p, const int32_t *in, int32_t *out, size_t 
                        cudaStream_t st);
 int launch_gs_range_scatter(nttb200_plan *p, int32_t *d_buf, int sb, int se, void *const *peers,
                             int world, int rank, cudaStream_t st);
+int rns_launch(int sm_count, int kind, const uint4 *d_tw_tile, const uint4 *h_pos, uint32_t limbs,
+               const int32_t *d_a, const int32_t *d_b, int32_t *d_out, size_t batch,
+               cudaStream_t st);
+uint32_t rns_inv_mod_2_32(uint32_t q);
+constexpr int kRnsTwTile = 32 * 65;  // uint4s per channel in d_tw_tile (kernels_multi.cu)
 int launch_multi_ct(nttb200_plan *p, const int32_t *d_in, int32_t *d_out, size_t batch,
                     cudaStream_t st);
 int launch_multi_gs_dual(nttb200_plan *p, const int32_t *d_a, const int32_t *d_b, int32_t *d_out,

@@ -384,3 +384,66 @@ def test_extreme_moduli_on_fast_paths(lib, oracle_mod, logn):
                 plan.ct(d_in, d_out, 4)
                 assert "ct" in plan.last_path
             assert np.array_equal(d_out.cpu().numpy(), oracle_mod.ntt_ct(a, table, q)), (logn, q)
+
+
+def _ntt_primes(count, two_n=8192, below=1 << 30):
+    """Primes q < 2^30 with 2N | q-1, largest first (deterministic trial division)."""
+    out, k = [], (below - 1) // two_n
+    while len(out) < count and k > 0:
+        q = k * two_n + 1
+        if q < below and all(q % d for d in range(3, int(q ** 0.5) + 1, 2)) and q % 2:
+            out.append(q)
+        k -= 1
+    return out
+
+
+def _psi(n, q):
+    """An element of order 2n modulo the prime q."""
+    for x in range(2, 1000):
+        psi = pow(x, (q - 1) // (2 * n), q)
+        if pow(psi, n, q) == q - 1:
+            return psi
+    raise AssertionError("no 2n-th root found")
+
+
+def test_rns_batches(lib, oracle_mod):
+    """N=4096 polynomials in RNS form, [batch][L][4096], one launch for all
+    channels, each channel with its own prime and table.  GS and CT per channel against
+    the oracle; the negacyclic product per channel against the oracle pipeline and, for
+    one channel, the O(N^2) schoolbook product."""
+    n, limbs, batch = 4096, 5, 7
+    qs = _ntt_primes(limbs - 1) + [Q29]
+    rng = np.random.default_rng(13000)
+    fwd_t, inv_t = [], []
+    for q in qs:
+        psi = _psi(n, q)
+        fwd_t.append(lib.make_bitrev_table(n, q, psi))
+        inv_t.append(lib.make_bitrev_table(n, q, pow(psi, q - 2, q)))
+    a = np.stack([np.stack([rng.integers(0, q, n, dtype=np.int32) for q in qs]) for _ in range(batch)])
+    b = np.stack([np.stack([rng.integers(0, q, n, dtype=np.int32) for q in qs]) for _ in range(batch)])
+    a[0, :, :] = np.array(qs, dtype=np.int32)[:, None] - 1
+    d_a, d_b = dev(a), dev(b)
+    d_o = torch.empty_like(d_a)
+    with lib.RnsPlan(qs, fwd_t) as pf, lib.RnsPlan(qs, inv_t) as pi:
+        pi.gs(d_a, d_o, batch)
+        got = d_o.cpu().numpy()
+        for l, q in enumerate(qs):
+            assert np.array_equal(got[:, l], oracle_mod.ntt_gs(a[:, l], inv_t[l], q)), ("gs", l)
+        pf.ct(d_a, d_o, batch)
+        got = d_o.cpu().numpy()
+        for l, q in enumerate(qs):
+            assert np.array_equal(got[:, l], oracle_mod.ntt_ct(a[:, l], fwd_t[l], q)), ("ct", l)
+        lib.rns_polymul_negacyclic(pf, pi, d_a, d_b, d_o, batch)
+        got = d_o.cpu().numpy()
+        for l, q in enumerate(qs):
+            prod = oracle_mod.pointwise(oracle_mod.ntt_ct(a[:, l], fwd_t[l], q),
+                                        oracle_mod.ntt_ct(b[:, l], fwd_t[l], q), q)
+            want = oracle_mod.scale(oracle_mod.ntt_gs(prod, inv_t[l], q),
+                                    oracle_mod.powmod(n, q - 2, q), q)
+            assert np.array_equal(got[:, l], want), ("polymul", l)
+        assert np.array_equal(got[1, 0], oracle_mod.negacyclic_schoolbook(a[1, 0], b[1, 0], qs[0]))
+        # in place, and the operands were left untouched above
+        assert np.array_equal(d_a.cpu().numpy(), a)
+        pi.gs(d_a, d_a, batch)
+        for l, q in enumerate(qs):
+            assert np.array_equal(d_a.cpu().numpy()[:, l], oracle_mod.ntt_gs(a[:, l], inv_t[l], q))
