@@ -162,17 +162,18 @@ tile_gs_kernel(const __grid_constant__ CUtensorMap map_lo, const __grid_constant
     // Work: tiles in position-major order u = c * batch + poly, so that one CTA stays
     // on (at most two) tile positions and their twiddles stay in L1.  CTA b owns the
     // contiguous range [b*T/G, (b+1)*T/G); its teams stride through it.
+    // (the host guarantees batch * chunks < 2^31, so tile arithmetic stays 32-bit)
     const uint64_t total = (uint64_t) prm.batch * prm.chunks;
-    const uint64_t u_begin = total * blockIdx.x / gridDim.x;
-    const uint64_t u_end = total * (blockIdx.x + 1) / gridDim.x;
+    const uint32_t u_begin = (uint32_t) (total * blockIdx.x / gridDim.x);
+    const uint32_t u_end = (uint32_t) (total * (blockIdx.x + 1) / gridDim.x);
     const uint32_t buf = data_base + team * kF_PolyBytes;
     const uint32_t bar = bar_base + team * 8;
     uint32_t parity = 0;
-    uint64_t u = u_begin + team;
+    uint32_t u = u_begin + team;
 
-    auto tile_of = [&](uint64_t uu, uint32_t &c) -> uint32_t {
-        c = (uint32_t) (uu / prm.batch);
-        uint32_t poly = (uint32_t) (uu - (uint64_t) c * prm.batch);
+    auto tile_of = [&](uint32_t uu, uint32_t &c) -> uint32_t {
+        c = uu / prm.batch;
+        uint32_t poly = uu - c * prm.batch;
         return poly * prm.chunks + c;  // tile index in memory
     };
 
@@ -254,7 +255,7 @@ tile_gs_kernel(const __grid_constant__ CUtensorMap map_lo, const __grid_constant
         team_sync(team);
 
         const uint32_t tile_store = tile_cur;
-        const uint64_t next = u + kM_Teams;
+        const uint32_t next = u + kM_Teams;
         if (next < u_end) {
             tile_cur = tile_of(next, c_cur);
             if (j == 0) {
@@ -304,16 +305,17 @@ tile_ct_kernel(const __grid_constant__ CUtensorMap map_lo, const __grid_constant
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     __syncthreads();
 
+    // (the host guarantees batch * chunks < 2^31, so tile arithmetic stays 32-bit)
     const uint64_t total = (uint64_t) prm.batch * prm.chunks;
-    const uint64_t u_begin = total * blockIdx.x / gridDim.x;
-    const uint64_t u_end = total * (blockIdx.x + 1) / gridDim.x;
+    const uint32_t u_begin = (uint32_t) (total * blockIdx.x / gridDim.x);
+    const uint32_t u_end = (uint32_t) (total * (blockIdx.x + 1) / gridDim.x);
     const uint32_t buf = data_base + team * kF_PolyBytes;
     const uint32_t bar = bar_base + team * 8;
     uint32_t parity = 0;
-    uint64_t u = u_begin + team;
-    auto tile_of = [&](uint64_t uu, uint32_t &c) -> uint32_t {
-        c = (uint32_t) (uu / prm.batch);
-        uint32_t poly = (uint32_t) (uu - (uint64_t) c * prm.batch);
+    uint32_t u = u_begin + team;
+    auto tile_of = [&](uint32_t uu, uint32_t &c) -> uint32_t {
+        c = uu / prm.batch;
+        uint32_t poly = uu - c * prm.batch;
         return poly * prm.chunks + c;
     };
     uint32_t c_cur = 0, tile_cur = 0;
@@ -391,7 +393,7 @@ tile_ct_kernel(const __grid_constant__ CUtensorMap map_lo, const __grid_constant
         }
         fence_proxy_async();
         team_sync(team);
-        const uint64_t next = u + kM_Teams;
+        const uint32_t next = u + kM_Teams;
         uint32_t tile_next = 0;
         if (next < u_end) tile_next = tile_of(next, c_cur);
         if (j == 0) {
