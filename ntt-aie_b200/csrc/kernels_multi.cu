@@ -281,6 +281,172 @@ tile_gs_kernel(const __grid_constant__ CUtensorMap map_lo, const __grid_constant
     }
 }
 
+// N = 2^13 .. 2^15 in ONE pass: the G = N/4096 tiles of a polynomial are taken by G
+// teams of the same CTA at the same time.  Each team runs the two register rounds of
+// its tile (stages 0-11) exactly as above; then a third round exchanges through the G
+// tile buffers (every thread keeps 64/G register rows of ALL G tiles) and runs the
+// last log2 G stages -- the cross-tile stages -- in registers, so no second HBM pass
+// is needed.  Successor of the reference's cross-tile ntt_1stage calls
+// (src/aie_core.cc:161-187, src/aie2.py:184-295) with a group barrier in the role of
+// the lock fifos (src/aie2.py:128-154).
+template <int LOGG, bool DUAL>
+__global__ void __launch_bounds__(kM_Threads, 1)
+poly_gs_kernel(const __grid_constant__ CUtensorMap map_lo, const __grid_constant__ CUtensorMap map_hi,
+               const __grid_constant__ CUtensorMap map_b_lo,
+               const __grid_constant__ CUtensorMap map_b_hi, const TileParams prm,
+               const uint2 *__restrict__ tw_flat) {
+    constexpr int G = 1 << LOGG;           // tiles = teams per polynomial
+    constexpr int kGroups = kM_Teams / G;  // polynomials in flight per CTA
+    constexpr int kSlice = 64 / G;         // register rows a thread keeps in round 3
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t data_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    const uint32_t bar_base = data_base + kM_Teams * kF_PolyBytes;
+    const int tid = threadIdx.x;
+    const int team = __shfl_sync(0xffffffffu, tid >> 6, 0);  // warp-uniform for the compiler
+    const int j = tid & 63;
+    const int grp = team >> LOGG, t = team & (G - 1);
+    const uint32_t q = prm.q, two_q = 2u * prm.q, zero = prm.zero;
+
+    if (tid < kM_Teams) mbar_init(bar_base + tid * 8, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    __syncthreads();
+
+    const uint32_t buf = data_base + team * kF_PolyBytes;
+    const uint32_t gbuf = data_base + (grp << LOGG) * kF_PolyBytes;
+    const uint32_t bar = bar_base + team * 8;
+    const uint32_t stride = gridDim.x * kGroups;
+    uint32_t poly = blockIdx.x * kGroups + grp;
+    uint32_t parity = 0;
+    if (j == 0 && poly < prm.batch) {
+        mbar_expect_tx(bar, kF_PolyBytes);
+        tma_load_3d(buf, &map_lo, bar, 0, 0, (int) (poly * G + t));
+        tma_load_3d(buf + kF_PolyBytes / 2, &map_hi, bar, 0, 0, (int) (poly * G + t));
+    }
+    const uint32_t r1_row = buf + j * 128;
+    const uint32_t r1_xor = (j & 7) << 4;
+    const uint32_t r2_col = buf + (j >> 5) * (kF_PolyBytes / 2) + (j & 3) * 4;
+    const uint32_t r2_chunk = ((j & 31) >> 2) << 4;
+    const uint4 *tw = prm.tw_tile + (size_t) t * kM_TwTile;
+    auto group_sync = [&]() {
+        asm volatile("bar.sync %0, %1;" ::"r"(9 + grp), "n"(G * 64) : "memory");
+    };
+
+    for (; poly < prm.batch; poly += stride) {
+        uint32_t v[64];
+        const int tile = (int) (poly * G + t);
+        mbar_wait(bar, parity);
+        parity ^= 1;
+#pragma unroll
+        for (int c = 0; c < 16; c++) {
+            uint4 x = lds128(r1_row + (c >> 3) * (kF_PolyBytes / 2) + (((c & 7) << 4) ^ r1_xor));
+            v[4 * c + 0] = x.x;
+            v[4 * c + 1] = x.y;
+            v[4 * c + 2] = x.z;
+            v[4 * c + 3] = x.w;
+        }
+        if (DUAL) {
+            team_sync(team);
+            if (j == 0) {
+                mbar_expect_tx(bar, kF_PolyBytes);
+                tma_load_3d(buf, &map_b_lo, bar, 0, 0, tile);
+                tma_load_3d(buf + kF_PolyBytes / 2, &map_b_hi, bar, 0, 0, tile);
+            }
+            mbar_wait(bar, parity);
+            parity ^= 1;
+#pragma unroll
+            for (int c = 0; c < 16; c++) {
+                uint4 x = lds128(r1_row + (c >> 3) * (kF_PolyBytes / 2) + (((c & 7) << 4) ^ r1_xor));
+                const uint32_t bb[4] = {x.x, x.y, x.z, x.w};
+#pragma unroll
+                for (int e = 0; e < 4; e++) {
+                    uint64_t prod = (uint64_t) v[4 * c + e] * bb[e];
+                    uint32_t m = (uint32_t) prod * prm.qinv;
+                    v[4 * c + e] = (uint32_t) (prod >> 32) - __umulhi(m, q) + q;
+                }
+            }
+        }
+        const uint4 *tw1 = tw + j;
+        gs_stage_g<0, DUAL>(v, tw1, q, two_q, zero);
+        gs_stage_g<1, true>(v, tw1, q, two_q, zero);
+        gs_stage_g<2, true>(v, tw1, q, two_q, zero);
+        gs_stage_g<3, true>(v, tw1, q, two_q, zero);
+        gs_stage_g<4, true>(v, tw1, q, two_q, zero);
+        gs_stage_g<5, true>(v, tw1, q, two_q, zero);
+#pragma unroll
+        for (int c = 0; c < 16; c++) {
+            sts128(r1_row + (c >> 3) * (kF_PolyBytes / 2) + (((c & 7) << 4) ^ r1_xor), v[4 * c],
+                   v[4 * c + 1], v[4 * c + 2], v[4 * c + 3]);
+        }
+        team_sync(team);
+#pragma unroll
+        for (int i = 0; i < 64; i++) {
+            v[i] = lds32(r2_col + i * 128 + (r2_chunk ^ ((i & 7) << 4)));
+        }
+        team_sync(team);
+        const uint4 *tw2 = tw + 64;
+        gs_stage_g<0, true>(v, tw2, q, two_q, zero);
+        gs_stage_g<1, true>(v, tw2, q, two_q, zero);
+        gs_stage_g<2, true>(v, tw2, q, two_q, zero);
+        gs_stage_g<3, true>(v, tw2, q, two_q, zero);
+        gs_stage_g<4, true>(v, tw2, q, two_q, zero);
+        gs_stage_g<5, true>(v, tw2, q, two_q, zero);
+
+        // ---- round 3: register i is a[t*4096 + j + 64 i].  Park it at [i][j] of this
+        // team's buffer, then collect rows t*kSlice .. +kSlice-1 of ALL G tiles.
+#pragma unroll
+        for (int i = 0; i < 64; i++) {
+            asm volatile("st.shared.u32 [%0], %1;" ::"r"(buf + (i * 64 + j) * 4), "r"(v[i]) : "memory");
+        }
+        group_sync();
+        uint32_t w[64];
+#pragma unroll
+        for (int tt = 0; tt < G; tt++) {
+#pragma unroll
+            for (int ii = 0; ii < kSlice; ii++) {
+                w[tt * kSlice + ii] =
+                    lds32(gbuf + tt * kF_PolyBytes + (((t * kSlice + ii) * 64 + j) << 2));
+            }
+        }
+        fence_proxy_async();
+        group_sync();
+        // ---- every buffer of the group is free: prefetch this team's next tile
+        const uint32_t next = poly + stride;
+        if (j == 0 && next < prm.batch) {
+            mbar_expect_tx(bar, kF_PolyBytes);
+            tma_load_3d(buf, &map_lo, bar, 0, 0, (int) (next * G + t));
+            tma_load_3d(buf + kF_PolyBytes / 2, &map_hi, bar, 0, 0, (int) (next * G + t));
+        }
+        // ---- stages 12 .. 12+LOGG-1 pair tiles tt and tt + 2^m; twiddle
+        //      table[(G >> (m+1)) + (tt >> (m+1))], the same for every thread
+#pragma unroll
+        for (int m = 0; m < LOGG; m++) {
+#pragma unroll
+            for (int b2 = 0; b2 < (G >> (m + 1)); b2++) {
+                const uint2 tq = __ldg(tw_flat + (G >> (m + 1)) + b2);
+#pragma unroll
+                for (int e = 0; e < (1 << m); e++) {
+                    const int t0 = (b2 << (m + 1)) + e;
+#pragma unroll
+                    for (int ii = 0; ii < kSlice; ii++) {
+                        gs_bfly<true>(w[t0 * kSlice + ii], w[(t0 + (1 << m)) * kSlice + ii], tq.x, tq.y,
+                                      q, two_q, zero);
+                    }
+                }
+            }
+        }
+        uint32_t *dst = prm.out + ((size_t) poly << (12 + LOGG)) + j + 64 * (t * kSlice);
+#pragma unroll
+        for (int tt = 0; tt < G; tt++) {
+#pragma unroll
+            for (int ii = 0; ii < kSlice; ii++) {
+                uint32_t r = w[tt * kSlice + ii];
+                if (DUAL) r = shoup_mul_lazy(r, prm.scale, prm.scale_shoup, q);
+                dst[tt * 4096 + ii * 64] = min(r - q, r);
+            }
+        }
+    }
+}
+
 // Forward partner: CT stages 11..0 of every tile (stride 2048 -> 1).  Columns first
 // (uniform twiddles), exchange, rows (thread-private twiddles); the rows go back to the
 // team's buffer and leave through a TMA store.
@@ -529,6 +695,12 @@ int multi_set_attrs() {
     NTTB200_CUDA(cudaFuncSetAttribute(tile_gs_kernel<true, true>, attr, kM_SmemBytes));
     NTTB200_CUDA(cudaFuncSetAttribute(tile_ct_kernel<false>, attr, kM_SmemBytes));
     NTTB200_CUDA(cudaFuncSetAttribute(tile_ct_kernel<true>, attr, kM_SmemBytes));
+    NTTB200_CUDA(cudaFuncSetAttribute(poly_gs_kernel<1, false>, attr, kM_SmemBytes));
+    NTTB200_CUDA(cudaFuncSetAttribute(poly_gs_kernel<2, false>, attr, kM_SmemBytes));
+    NTTB200_CUDA(cudaFuncSetAttribute(poly_gs_kernel<3, false>, attr, kM_SmemBytes));
+    NTTB200_CUDA(cudaFuncSetAttribute(poly_gs_kernel<1, true>, attr, kM_SmemBytes));
+    NTTB200_CUDA(cudaFuncSetAttribute(poly_gs_kernel<2, true>, attr, kM_SmemBytes));
+    NTTB200_CUDA(cudaFuncSetAttribute(poly_gs_kernel<3, true>, attr, kM_SmemBytes));
     return NTTB200_OK;
 }
 
@@ -639,6 +811,55 @@ static int tile_grid(nttb200_plan *p, uint64_t tiles) {
     return (int) (ctas < (uint64_t) p->sm_count ? ctas : (uint64_t) p->sm_count);
 }
 
+template <int LOGG, bool DUAL>
+static void poly_launch_t(int grid, cudaStream_t st, const CUtensorMap &a_lo, const CUtensorMap &a_hi,
+                          const CUtensorMap &b_lo, const CUtensorMap &b_hi, const TileParams &tp,
+                          const uint2 *tw) {
+    poly_gs_kernel<LOGG, DUAL><<<grid, kM_Threads, kM_SmemBytes, st>>>(a_lo, a_hi, b_lo, b_hi, tp, tw);
+}
+
+static bool poly_kernel_enabled() {
+    static const bool on = getenv("NTTB200_NO_POLY_KERNEL") == nullptr;
+    return on;
+}
+
+// N = 2^13..2^15 in one pass (poly_gs_kernel).  d_b != nullptr: input = d_in (*) d_b,
+// output scaled by N^-1.
+static int launch_poly_gs(nttb200_plan *p, const int32_t *d_in, const int32_t *d_b, int32_t *d_out,
+                          size_t batch, cudaStream_t st) {
+    const int logg = (int) p->logn - 12;
+    if (logg < 1 || logg > 3 || !poly_kernel_enabled()) return NTTB200_ERR_UNSUPPORTED;
+    const uint64_t tiles = (uint64_t) batch << logg;
+    CUtensorMap a_lo, a_hi, b_lo, b_hi;
+    if (tile_maps(&a_lo, &a_hi, d_in, (size_t) tiles) != NTTB200_OK) return NTTB200_ERR_UNSUPPORTED;
+    TileParams tp = tile_params(p, d_out, batch);
+    if (d_b) {
+        if (tile_maps(&b_lo, &b_hi, d_b, (size_t) tiles) != NTTB200_OK) return NTTB200_ERR_UNSUPPORTED;
+        tp.qinv = inv_mod_2_32(p->q);
+        uint64_t sc = ((uint64_t) p->n_inv << 32) % p->q;
+        tp.scale = (uint32_t) sc;
+        tp.scale_shoup = (uint32_t) ((sc << 32) / p->q);
+    } else {
+        b_lo = a_lo;
+        b_hi = a_hi;
+    }
+    const uint64_t groups = kM_Teams >> logg;
+    uint64_t ctas = (batch + groups - 1) / groups;
+    int grid = (int) (ctas < (uint64_t) p->sm_count ? ctas : (uint64_t) p->sm_count);
+    const bool dual = d_b != nullptr;
+    switch (logg * 2 + (dual ? 1 : 0)) {
+        case 2: poly_launch_t<1, false>(grid, st, a_lo, a_hi, b_lo, b_hi, tp, p->d_tw); break;
+        case 3: poly_launch_t<1, true>(grid, st, a_lo, a_hi, b_lo, b_hi, tp, p->d_tw); break;
+        case 4: poly_launch_t<2, false>(grid, st, a_lo, a_hi, b_lo, b_hi, tp, p->d_tw); break;
+        case 5: poly_launch_t<2, true>(grid, st, a_lo, a_hi, b_lo, b_hi, tp, p->d_tw); break;
+        case 6: poly_launch_t<3, false>(grid, st, a_lo, a_hi, b_lo, b_hi, tp, p->d_tw); break;
+        default: poly_launch_t<3, true>(grid, st, a_lo, a_hi, b_lo, b_hi, tp, p->d_tw); break;
+    }
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+    NTTB200_CUDA(cudaGetLastError());
+    return NTTB200_OK;
+}
+
 // d_b == nullptr: plain transform of d_in.  Otherwise the input is d_in (*) d_b and the
 // output is scaled by N^-1 (inverse transform of a negacyclic product).
 static int launch_multi_gs_once(nttb200_plan *p, const int32_t *d_in, const int32_t *d_b,
@@ -691,6 +912,11 @@ int launch_multi_gs(nttb200_plan *p, const int32_t *d_in, int32_t *d_out, size_t
     // L2 blocking: run the passes over sub-batches small enough that what the tile
     // pass writes is still in the 126 MB L2 when the column pass reads it, so the
     // intermediate never costs HBM bandwidth.
+    {
+        int rc = launch_poly_gs(p, d_in, nullptr, d_out, batch, st);
+        if (rc == NTTB200_OK) p->last_path = "poly_tma_3round";
+        if (rc != NTTB200_ERR_UNSUPPORTED) return rc;
+    }
     static const long l2_mb = []() {
         const char *e = getenv("NTTB200_L2_CHUNK_MB");
         return e ? atol(e) : 0L;  // measured: separate sub-batch launches lose more than L2 hits win
@@ -779,7 +1005,10 @@ int launch_multi_gs_dual(nttb200_plan *p, const int32_t *d_a, const int32_t *d_b
         return NTTB200_ERR_UNSUPPORTED;
     }
     if (batch == 0) return NTTB200_OK;
-    int rc = launch_multi_gs_once(p, d_a, d_b, d_out, batch, st);
+    int rc = launch_poly_gs(p, d_a, d_b, d_out, batch, st);
+    if (rc == NTTB200_OK) p->last_path = "poly_tma_3round_dual";
+    if (rc != NTTB200_ERR_UNSUPPORTED) return rc;
+    rc = launch_multi_gs_once(p, d_a, d_b, d_out, batch, st);
     if (rc == NTTB200_OK) p->last_path = "tile_tma_dual + column_passes";
     return rc;
 }

@@ -334,7 +334,7 @@ def test_large_n_multi_pass_path(lib, oracle_mod, logn):
     for batch in ((1, 3, 40) if logn <= 16 else (1, 2)):
         a = rng.integers(0, Q29, (batch, n), dtype=np.int32)
         out, path = run_gs(lib, a, table, Q29)
-        assert "tile" in path, path
+        assert "tile" in path or "poly" in path, path
         assert np.array_equal(out, oracle_mod.ntt_gs(a, table, Q29)), (logn, batch)
         out, _ = run_gs(lib, a, table, Q29, inplace=True)
         assert np.array_equal(out, oracle_mod.ntt_gs(a, table, Q29)), (logn, batch, "in place")
