@@ -580,6 +580,165 @@ tile_ct_kernel(const __grid_constant__ CUtensorMap map_lo, const __grid_constant
     // registers -- measured in the SASS.)
 }
 
+// Forward partner of poly_gs_kernel: N = 2^13..2^15 in one pass.  The cross-tile stages
+// come FIRST in the CT order (largest strides): once the G tiles of a polynomial have
+// landed, every thread gathers its slice of rows from all G tile buffers, runs stages
+// logn-1 .. 12 in registers and puts the values back; then each team finishes its own
+// tile exactly like tile_ct_kernel.
+template <int LOGG>
+__global__ void __launch_bounds__(kM_Threads, 1)
+poly_ct_kernel(const __grid_constant__ CUtensorMap map_lo, const __grid_constant__ CUtensorMap map_hi,
+               const __grid_constant__ CUtensorMap out_lo, const __grid_constant__ CUtensorMap out_hi,
+               const TileParams prm, const uint2 *__restrict__ tw_flat) {
+    constexpr int G = 1 << LOGG;
+    constexpr int kGroups = kM_Teams / G;
+    constexpr int kSlice = 64 / G;
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t data_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    const uint32_t bar_base = data_base + kM_Teams * kF_PolyBytes;
+    const int tid = threadIdx.x;
+    const int team = __shfl_sync(0xffffffffu, tid >> 6, 0);
+    const int j = tid & 63;
+    const int grp = team >> LOGG, t = team & (G - 1);
+    const uint32_t q = prm.q, two_q = 2u * prm.q, zero = prm.zero;
+
+    if (tid < kM_Teams) mbar_init(bar_base + tid * 8, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    __syncthreads();
+
+    const uint32_t buf = data_base + team * kF_PolyBytes;
+    const uint32_t gbuf = data_base + (grp << LOGG) * kF_PolyBytes;
+    const uint32_t bar = bar_base + team * 8;
+    const uint32_t stride = gridDim.x * kGroups;
+    uint32_t poly = blockIdx.x * kGroups + grp;
+    uint32_t parity = 0;
+    if (j == 0 && poly < prm.batch) {
+        mbar_expect_tx(bar, kF_PolyBytes);
+        tma_load_3d(buf, &map_lo, bar, 0, 0, (int) (poly * G + t));
+        tma_load_3d(buf + kF_PolyBytes / 2, &map_hi, bar, 0, 0, (int) (poly * G + t));
+    }
+    const uint32_t r1_row = buf + j * 128;
+    const uint32_t r1_xor = (j & 7) << 4;
+    const uint32_t col_off = (j >> 5) * (kF_PolyBytes / 2) + (j & 3) * 4;  // column j of a tile buffer
+    const uint32_t r2_col = buf + col_off;
+    const uint32_t r2_chunk = ((j & 31) >> 2) << 4;
+    const uint4 *tw = prm.tw_tile + (size_t) t * kM_TwTile;
+    auto group_sync = [&]() {
+        asm volatile("bar.sync %0, %1;" ::"r"(9 + grp), "n"(G * 64) : "memory");
+    };
+
+    for (; poly < prm.batch; poly += stride) {
+        uint32_t v[64];
+        const int tile = (int) (poly * G + t);
+        mbar_wait(bar, parity);
+        parity ^= 1;
+        group_sync();  // all G tiles of the polynomial are in shared memory
+        // ---- cross-tile stages logn-1 .. 12 on rows t*kSlice .. +kSlice-1 of every tile
+#pragma unroll
+        for (int tt = 0; tt < G; tt++) {
+#pragma unroll
+            for (int ii = 0; ii < kSlice; ii++) {
+                const int i = t * kSlice + ii;  // not a compile-time constant: t is per team
+                v[tt * kSlice + ii] = lds32(gbuf + tt * kF_PolyBytes + col_off + i * 128 +
+                                            (r2_chunk ^ ((i & 7) << 4)));
+            }
+        }
+#pragma unroll
+        for (int mm = 0; mm < LOGG; mm++) {
+            const int m = LOGG - 1 - mm;
+#pragma unroll
+            for (int b2 = 0; b2 < (G >> (m + 1)); b2++) {
+                const uint2 tq = __ldg(tw_flat + (G >> (m + 1)) + b2);
+#pragma unroll
+                for (int e = 0; e < (1 << m); e++) {
+                    const int t0 = (b2 << (m + 1)) + e;
+#pragma unroll
+                    for (int ii = 0; ii < kSlice; ii++) {
+                        if (mm == 0) {
+                            ct_bfly<false>(v[t0 * kSlice + ii], v[(t0 + (1 << m)) * kSlice + ii], tq.x,
+                                           tq.y, q, two_q, zero);
+                        } else {
+                            ct_bfly<true>(v[t0 * kSlice + ii], v[(t0 + (1 << m)) * kSlice + ii], tq.x,
+                                          tq.y, q, two_q, zero);
+                        }
+                    }
+                }
+            }
+        }
+#pragma unroll
+        for (int tt = 0; tt < G; tt++) {
+#pragma unroll
+            for (int ii = 0; ii < kSlice; ii++) {
+                const int i = t * kSlice + ii;
+                asm volatile("st.shared.u32 [%0], %1;" ::"r"(gbuf + tt * kF_PolyBytes + col_off + i * 128 +
+                                                             (r2_chunk ^ ((i & 7) << 4))),
+                             "r"(v[tt * kSlice + ii])
+                             : "memory");
+            }
+        }
+        group_sync();
+        // ---- this team's tile: columns (stages 11..6), exchange, rows (stages 5..0)
+#pragma unroll
+        for (int i = 0; i < 64; i++) {
+            v[i] = lds32(r2_col + i * 128 + (r2_chunk ^ ((i & 7) << 4)));
+        }
+        const uint4 *tw2 = tw + 64;
+        ct_stage_g<5, true>(v, tw2, q, two_q, zero);
+        ct_stage_g<4, true>(v, tw2, q, two_q, zero);
+        ct_stage_g<3, true>(v, tw2, q, two_q, zero);
+        ct_stage_g<2, true>(v, tw2, q, two_q, zero);
+        ct_stage_g<1, true>(v, tw2, q, two_q, zero);
+        ct_stage_g<0, true>(v, tw2, q, two_q, zero);
+#pragma unroll
+        for (int i = 0; i < 64; i++) {
+            asm volatile("st.shared.u32 [%0], %1;" ::"r"(r2_col + i * 128 + (r2_chunk ^ ((i & 7) << 4))),
+                         "r"(v[i])
+                         : "memory");
+        }
+        team_sync(team);
+#pragma unroll
+        for (int c = 0; c < 16; c++) {
+            uint4 x = lds128(r1_row + (c >> 3) * (kF_PolyBytes / 2) + (((c & 7) << 4) ^ r1_xor));
+            v[4 * c + 0] = x.x;
+            v[4 * c + 1] = x.y;
+            v[4 * c + 2] = x.z;
+            v[4 * c + 3] = x.w;
+        }
+        const uint4 *tw1 = tw + j;
+        ct_stage_g<5, true>(v, tw1, q, two_q, zero);
+        ct_stage_g<4, true>(v, tw1, q, two_q, zero);
+        ct_stage_g<3, true>(v, tw1, q, two_q, zero);
+        ct_stage_g<2, true>(v, tw1, q, two_q, zero);
+        ct_stage_g<1, true>(v, tw1, q, two_q, zero);
+        ct_stage_g<0, true>(v, tw1, q, two_q, zero);
+#pragma unroll
+        for (int c = 0; c < 16; c++) {
+            uint32_t o[4];
+#pragma unroll
+            for (int e = 0; e < 4; e++) {
+                uint32_t r = v[4 * c + e];
+                r = min(r - two_q, r);
+                o[e] = min(r - q, r);
+            }
+            sts128(r1_row + (c >> 3) * (kF_PolyBytes / 2) + (((c & 7) << 4) ^ r1_xor), o[0], o[1],
+                   o[2], o[3]);
+        }
+        fence_proxy_async();
+        team_sync(team);
+        const uint32_t next = poly + stride;
+        if (j == 0) {
+            tma_store_3d(&out_lo, buf, 0, 0, tile);
+            tma_store_3d(&out_hi, buf + kF_PolyBytes / 2, 0, 0, tile);
+            tma_store_commit_and_wait_read();
+            if (next < prm.batch) {
+                mbar_expect_tx(bar, kF_PolyBytes);
+                tma_load_3d(buf, &map_lo, bar, 0, 0, (int) (next * G + t));
+                tma_load_3d(buf + kF_PolyBytes / 2, &map_hi, bar, 0, 0, (int) (next * G + t));
+            }
+        }
+    }
+}
+
 // ------------------------------------------------------------------ column pass
 struct ColParams {
     uint32_t logn;
@@ -695,6 +854,9 @@ int multi_set_attrs() {
     NTTB200_CUDA(cudaFuncSetAttribute(tile_gs_kernel<true, true>, attr, kM_SmemBytes));
     NTTB200_CUDA(cudaFuncSetAttribute(tile_ct_kernel<false>, attr, kM_SmemBytes));
     NTTB200_CUDA(cudaFuncSetAttribute(tile_ct_kernel<true>, attr, kM_SmemBytes));
+    NTTB200_CUDA(cudaFuncSetAttribute(poly_ct_kernel<1>, attr, kM_SmemBytes));
+    NTTB200_CUDA(cudaFuncSetAttribute(poly_ct_kernel<2>, attr, kM_SmemBytes));
+    NTTB200_CUDA(cudaFuncSetAttribute(poly_ct_kernel<3>, attr, kM_SmemBytes));
     NTTB200_CUDA(cudaFuncSetAttribute(poly_gs_kernel<1, false>, attr, kM_SmemBytes));
     NTTB200_CUDA(cudaFuncSetAttribute(poly_gs_kernel<2, false>, attr, kM_SmemBytes));
     NTTB200_CUDA(cudaFuncSetAttribute(poly_gs_kernel<3, false>, attr, kM_SmemBytes));
@@ -1019,6 +1181,30 @@ int launch_multi_ct(nttb200_plan *p, const int32_t *d_in, int32_t *d_out, size_t
                     cudaStream_t st) {
     if (!multi_args_ok(p, d_in, d_out, batch)) return NTTB200_ERR_UNSUPPORTED;
     if (batch == 0) return NTTB200_OK;
+    const int logg = (int) p->logn - 12;
+    if (logg >= 1 && logg <= 3 && poly_kernel_enabled()) {
+        // N = 2^13..2^15: one pass, cross-tile stages inside the CTA
+        const uint64_t ptiles = (uint64_t) batch << logg;
+        CUtensorMap i_lo, i_hi, o_lo, o_hi;
+        if (tile_maps(&i_lo, &i_hi, d_in, (size_t) ptiles) == NTTB200_OK &&
+            tile_maps(&o_lo, &o_hi, d_out, (size_t) ptiles) == NTTB200_OK) {
+            TileParams tp = tile_params(p, d_out, batch);
+            const uint64_t groups = kM_Teams >> logg;
+            uint64_t ctas = (batch + groups - 1) / groups;
+            int grid = (int) (ctas < (uint64_t) p->sm_count ? ctas : (uint64_t) p->sm_count);
+            if (logg == 1) {
+                poly_ct_kernel<1><<<grid, kM_Threads, kM_SmemBytes, st>>>(i_lo, i_hi, o_lo, o_hi, tp, p->d_tw);
+            } else if (logg == 2) {
+                poly_ct_kernel<2><<<grid, kM_Threads, kM_SmemBytes, st>>>(i_lo, i_hi, o_lo, o_hi, tp, p->d_tw);
+            } else {
+                poly_ct_kernel<3><<<grid, kM_Threads, kM_SmemBytes, st>>>(i_lo, i_hi, o_lo, o_hi, tp, p->d_tw);
+            }
+            g_launches.fetch_add(1, std::memory_order_relaxed);
+            NTTB200_CUDA(cudaGetLastError());
+            p->last_path = "poly_tma_3round_ct";
+            return NTTB200_OK;
+        }
+    }
     const int32_t *src = d_in;
     int rest = (int) p->logn - 12;
     int passes = (rest + 5) / 6;
