@@ -255,6 +255,17 @@ int nttb200_ct_batch(nttb200_plan *p, const int32_t *d_in, int32_t *d_out, size_
     if (full && !(p->flags & NTTB200_FORCE_GENERIC)) {
         int rc = launch_multi_ct(p, d_in, d_out, batch, (cudaStream_t) stream);
         if (rc != NTTB200_ERR_UNSUPPORTED) return rc;
+        size_t done = 0;
+        rc = launch_small(p, 3, d_in, nullptr, d_out, batch, (cudaStream_t) stream, &done);
+        if (rc == NTTB200_OK) {
+            if (done == batch) return rc;
+            const char *path = p->last_path;  // ragged tail through the generic pass
+            rc = launch_generic(p, d_in + done * p->n, d_out + done * p->n, batch - done, 0,
+                                (int) p->logn, true, false, (cudaStream_t) stream);
+            p->last_path = path;
+            return rc;
+        }
+        if (rc != NTTB200_ERR_UNSUPPORTED) return rc;
     }
     p->last_path = "generic_stage_pass";
     return launch_generic(p, d_in, d_out, batch, sb, (int) p->logn, /*ct=*/true, false,
@@ -403,6 +414,21 @@ int nttb200_polymul_negacyclic(nttb200_plan *fwd, nttb200_plan *inv, const int32
             return rc;
         }
         tmp = nullptr;  // fall through to the generic pipeline (nothing was written to d_c)
+    }
+    if (!((fwd->flags | inv->flags) & NTTB200_FORCE_GENERIC) && fwd->logn >= 9 && fwd->logn <= 11 &&
+        fwd->d_tw_r1 && inv->d_tw_r1 && batch % ((size_t) 2048 >> fwd->logn) == 0) {
+        // N = 512..2048: warp-per-block CT, CT, then pointwise + inverse + scaling in one kernel
+        NTTB200_CUDA(cudaMallocAsync(&tmp, sizeof(int32_t) * words * 2, st));
+        size_t done = 0;
+        int rc = launch_small(fwd, 3, d_a, nullptr, tmp, batch, st, &done);
+        if (rc == NTTB200_OK) rc = launch_small(fwd, 3, d_b, nullptr, tmp + words, batch, st, &done);
+        if (rc == NTTB200_OK) rc = launch_small(inv, 2, tmp, tmp + words, d_c, batch, st, &done);
+        cudaError_t e = cudaFreeAsync(tmp, st);
+        if (rc != NTTB200_ERR_UNSUPPORTED) {
+            if (rc == NTTB200_OK && e != cudaSuccess) rc = cuda_fail(e, "cudaFreeAsync");
+            return rc;
+        }
+        tmp = nullptr;
     }
     NTTB200_CUDA(cudaMallocAsync(&tmp, sizeof(int32_t) * words, st));
     int rc = launch_generic(fwd, d_b, tmp, batch, 0, (int) fwd->logn, true, false, st);

@@ -60,18 +60,6 @@ __device__ __forceinline__ void gs_stage_g(uint32_t (&v)[64], const uint4 *tw, u
 }
 
 
-// Lazy Harvey Cooley-Tukey butterfly on values in [0, 4q): x is brought to [0, 2q),
-// v = y*w in [0, 2q) by Shoup; outputs x+v and x-v+2q, both in [0, 4q).  4q < 2^32.
-template <bool REDUCE_X>
-__device__ __forceinline__ void ct_bfly(uint32_t &x, uint32_t &y, uint32_t w, uint32_t wp,
-                                        uint32_t q, uint32_t two_q, uint32_t zero) {
-    uint32_t xr = REDUCE_X ? min(x - two_q, x) : x;
-    uint32_t h = __umulhi(y, wp);
-    uint32_t v = y * w - h * q;
-    x = xr + v + zero;
-    y = xr - v + two_q;
-}
-
 // CT stage on the thread's 64 registers (pairs i, i + 2^S), same twiddle slots as GS
 template <int S, bool REDUCE_X>
 __device__ __forceinline__ void ct_stage_g(uint32_t (&v)[64], const uint4 *tw, uint32_t q,
@@ -95,18 +83,6 @@ __device__ __forceinline__ void ct_stage_g(uint32_t (&v)[64], const uint4 *tw, u
             }
         }
     }
-}
-
-__device__ __forceinline__ void tma_store_3d(const CUtensorMap *map, uint32_t src, int c0, int c1,
-                                             int c2) {
-    asm volatile(
-        "cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];" ::"l"(map),
-        "r"(src), "r"(c0), "r"(c1), "r"(c2)
-        : "memory");
-}
-__device__ __forceinline__ void tma_store_commit_and_wait_read() {
-    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
-    asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
 }
 
 struct TileParams {

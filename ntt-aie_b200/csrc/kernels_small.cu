@@ -35,10 +35,13 @@ struct SmallParams {
     uint64_t blocks;      // 2048-coefficient blocks in the batch
     uint32_t q;
     uint32_t zero;
+    uint32_t qinv;        // DUAL: q^-1 mod 2^32 (Montgomery product of the two operands)
+    uint32_t scale;       // DUAL: every output times this constant (N^-1 * 2^32 mod q) ...
+    uint32_t scale_shoup; //       ... and its Shoup companion
 };
 
 // round-1 stage (same slot scheme as kernels_fused.cu, 32 lanes per slot)
-template <int S>
+template <int S, bool REDUCE0 = false>
 __device__ __forceinline__ void small_r1_stage(uint32_t (&v)[64], uint32_t tw_addr, uint32_t q,
                                                uint32_t two_q, uint32_t zero) {
     constexpr int kBlocks = 32 >> S;
@@ -50,13 +53,13 @@ __device__ __forceinline__ void small_r1_stage(uint32_t (&v)[64], uint32_t tw_ad
 #pragma unroll
         for (int e = 0; e < kStride; e++) {
             int i0 = b * 2 * kStride + e;
-            gs_bfly<(S > 0)>(v[i0], v[i0 + kStride], t.x, t.y, q, two_q, zero);
+            gs_bfly<(S > 0 || REDUCE0)>(v[i0], v[i0 + kStride], t.x, t.y, q, two_q, zero);
         }
         if (kBlocks >= 2) {
 #pragma unroll
             for (int e = 0; e < kStride; e++) {
                 int i0 = (b + 1) * 2 * kStride + e;
-                gs_bfly<(S > 0)>(v[i0], v[i0 + kStride], t.z, t.w, q, two_q, zero);
+                gs_bfly<(S > 0 || REDUCE0)>(v[i0], v[i0 + kStride], t.z, t.w, q, two_q, zero);
             }
         }
     }
@@ -80,10 +83,15 @@ __device__ __forceinline__ void small_r2_stage(uint32_t (&v)[64], const UniformT
     }
 }
 
-template <int LOGN, bool PERMUTE>
+// DUAL: the block's input is the pointwise product of two buffers (Montgomery product
+// a*b*2^-32, second operand through the same shared buffer) and every output is
+// multiplied by `scale` -- the tail of a negacyclic multiplication in one kernel.
+template <int LOGN, bool PERMUTE, bool DUAL>
 __global__ void __launch_bounds__(kS_Threads, 1)
 fused_gs_small_kernel(const __grid_constant__ CUtensorMap map_lo,
                       const __grid_constant__ CUtensorMap map_hi,
+                      const __grid_constant__ CUtensorMap map_b_lo,
+                      const __grid_constant__ CUtensorMap map_b_hi,
                       const __grid_constant__ UniformTw uni, const SmallParams prm) {
     extern __shared__ uint8_t smem_raw[];
     const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -134,7 +142,28 @@ fused_gs_small_kernel(const __grid_constant__ CUtensorMap map_lo,
             v[4 * c + 2] = t.z;
             v[4 * c + 3] = t.w;
         }
-        small_r1_stage<0>(v, tw_addr, q, two_q, zero);
+        if (DUAL) {
+            __syncwarp();
+            if (j == 0) {
+                mbar_expect_tx(bar, kS_BlockBytes);
+                tma_load_3d(buf, &map_b_lo, bar, 0, 0, (int) blk);
+                tma_load_3d(buf + kS_BlockBytes / 2, &map_b_hi, bar, 0, 0, (int) blk);
+            }
+            mbar_wait(bar, parity);
+            parity ^= 1;
+#pragma unroll
+            for (int c = 0; c < 16; c++) {
+                uint4 t = lds128(r1_row + (c >> 3) * (kS_BlockBytes / 2) + (((c & 7) << 4) ^ r1_xor));
+                const uint32_t bb[4] = {t.x, t.y, t.z, t.w};
+#pragma unroll
+                for (int e = 0; e < 4; e++) {
+                    uint64_t prod = (uint64_t) v[4 * c + e] * bb[e];
+                    uint32_t m = (uint32_t) prod * prm.qinv;
+                    v[4 * c + e] = (uint32_t) (prod >> 32) - __umulhi(m, q) + q;
+                }
+            }
+        }
+        small_r1_stage<0, DUAL>(v, tw_addr, q, two_q, zero);
         small_r1_stage<1>(v, tw_addr, q, two_q, zero);
         small_r1_stage<2>(v, tw_addr, q, two_q, zero);
         small_r1_stage<3>(v, tw_addr, q, two_q, zero);
@@ -178,11 +207,170 @@ fused_gs_small_kernel(const __grid_constant__ CUtensorMap map_lo,
                 b = ((b & 0x5) << 1) | ((b & 0xA) >> 1);
                 row = (b << 1) | (i & 1);
             }
+            uint32_t r0 = v[2 * i], r1 = v[2 * i + 1];
+            if (DUAL) {
+                r0 = shoup_mul_lazy(r0, prm.scale, prm.scale_shoup, q);
+                r1 = shoup_mul_lazy(r1, prm.scale, prm.scale_shoup, q);
+            }
             uint2 o;
-            o.x = min(v[2 * i] - q, v[2 * i]);
-            o.y = min(v[2 * i + 1] - q, v[2 * i + 1]);
+            o.x = min(r0 - q, r0);
+            o.y = min(r1 - q, r1);
             *reinterpret_cast<uint2 *>(dst + row * 64) = o;
         }
+    }
+}
+
+
+// round-2-type CT stage K (rows i, i + 2^K of both columns), uniform twiddles
+template <int LOGN, int K, bool REDUCE_X>
+__device__ __forceinline__ void small_ct_col_stage(uint32_t (&v)[64], const UniformTw &u, uint32_t q,
+                                                   uint32_t two_q, uint32_t zero) {
+    constexpr int RP = 1 << (LOGN - 6);
+#pragma unroll
+    for (int i = 0; i < 32; i++) {
+        if (i & (1 << K)) continue;
+        const int blk = (i & (RP - 1)) >> (K + 1);
+        const uint32_t w = u.w[(RP >> (K + 1)) + blk], wp = u.wp[(RP >> (K + 1)) + blk];
+#pragma unroll
+        for (int c = 0; c < 2; c++) {
+            ct_bfly<REDUCE_X>(v[2 * i + c], v[2 * (i + (1 << K)) + c], w, wp, q, two_q, zero);
+        }
+    }
+}
+
+// round-1-type CT stage S on 64 contiguous coefficients, thread-private twiddles
+template <int S, bool REDUCE_X>
+__device__ __forceinline__ void small_ct_row_stage(uint32_t (&v)[64], uint32_t tw_addr, uint32_t q,
+                                                   uint32_t two_q, uint32_t zero) {
+    constexpr int kBlocks = 32 >> S;
+    constexpr int kSlot0 = 32 - (kBlocks >= 2 ? kBlocks : 1);
+    constexpr int kStride = 1 << S;
+#pragma unroll
+    for (int b = 0; b < kBlocks; b += 2) {
+        uint4 t = lds128(tw_addr + (kSlot0 + b / 2) * (32 * 16));
+#pragma unroll
+        for (int e = 0; e < kStride; e++) {
+            int i0 = b * 2 * kStride + e;
+            ct_bfly<REDUCE_X>(v[i0], v[i0 + kStride], t.x, t.y, q, two_q, zero);
+        }
+        if (kBlocks >= 2) {
+#pragma unroll
+            for (int e = 0; e < kStride; e++) {
+                int i0 = (b + 1) * 2 * kStride + e;
+                ct_bfly<REDUCE_X>(v[i0], v[i0 + kStride], t.z, t.w, q, two_q, zero);
+            }
+        }
+    }
+}
+
+// Forward (Cooley-Tukey) partner, one warp per 2048-coefficient block: columns first
+// (stages logn-1 .. 6, uniform twiddles), warp-synchronous exchange, rows (stages 5 .. 0);
+// the canonical rows leave through a TMA store.
+template <int LOGN>
+__global__ void __launch_bounds__(kS_Threads, 1)
+fused_ct_small_kernel(const __grid_constant__ CUtensorMap map_lo,
+                      const __grid_constant__ CUtensorMap map_hi,
+                      const __grid_constant__ CUtensorMap out_lo,
+                      const __grid_constant__ CUtensorMap out_hi,
+                      const __grid_constant__ UniformTw uni, const SmallParams prm) {
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    const uint32_t tw_base = smem_base;
+    const uint32_t data_base = smem_base + kS_TwBytes;
+    const uint32_t bar_base = data_base + kS_Warps * kS_BlockBytes;
+    const int tid = threadIdx.x;
+    const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);
+    const int j = tid & 31;
+    const uint32_t q = prm.q, two_q = 2u * prm.q, zero = prm.zero;
+
+    for (int i = tid; i < 32 * 32; i += kS_Threads) {
+        uint4 t = __ldg(prm.tw_r1 + i);
+        sts128(tw_base + i * 16, t.x, t.y, t.z, t.w);
+    }
+    if (tid < kS_Warps) mbar_init(bar_base + tid * 8, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    __syncthreads();
+
+    const uint32_t buf = data_base + warp * kS_BlockBytes;
+    const uint32_t bar = bar_base + warp * 8;
+    const uint64_t stride = (uint64_t) gridDim.x * kS_Warps;
+    uint64_t blk = (uint64_t) blockIdx.x * kS_Warps + warp;
+    uint32_t parity = 0;
+    if (j == 0 && blk < prm.blocks) {
+        mbar_expect_tx(bar, kS_BlockBytes);
+        tma_load_3d(buf, &map_lo, bar, 0, 0, (int) blk);
+        tma_load_3d(buf + kS_BlockBytes / 2, &map_hi, bar, 0, 0, (int) blk);
+    }
+    const uint32_t r1_row = buf + j * 128;
+    const uint32_t r1_xor = (j & 7) << 4;
+    const uint32_t r2_col = buf + (j >> 4) * (kS_BlockBytes / 2) + (j & 1) * 8;
+    const uint32_t r2_chunk = ((j & 15) >> 1) << 4;
+    const uint32_t tw_addr = tw_base + j * 16;
+
+    for (; blk < prm.blocks; blk += stride) {
+        uint32_t v[64];
+        mbar_wait(bar, parity);
+        parity ^= 1;
+#pragma unroll
+        for (int i = 0; i < 32; i++) {
+            uint32_t addr = r2_col + i * 128 + (r2_chunk ^ ((i & 7) << 4));
+            asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];"
+                         : "=r"(v[2 * i]), "=r"(v[2 * i + 1])
+                         : "r"(addr));
+        }
+        // stages logn-1 .. 6: the first one sees canonical inputs
+        if (LOGN > 10) small_ct_col_stage<LOGN, 4, false>(v, uni, q, two_q, zero);
+        if (LOGN > 9) small_ct_col_stage<LOGN, 3, (LOGN > 10)>(v, uni, q, two_q, zero);
+        if (LOGN > 8) small_ct_col_stage<LOGN, 2, (LOGN > 9)>(v, uni, q, two_q, zero);
+        if (LOGN > 7) small_ct_col_stage<LOGN, 1, (LOGN > 8)>(v, uni, q, two_q, zero);
+        if (LOGN > 6) small_ct_col_stage<LOGN, 0, (LOGN > 7)>(v, uni, q, two_q, zero);
+#pragma unroll
+        for (int i = 0; i < 32; i++) {
+            uint32_t addr = r2_col + i * 128 + (r2_chunk ^ ((i & 7) << 4));
+            asm volatile("st.shared.v2.u32 [%0], {%1, %2};" ::"r"(addr), "r"(v[2 * i]), "r"(v[2 * i + 1])
+                         : "memory");
+        }
+        __syncwarp();
+#pragma unroll
+        for (int c = 0; c < 16; c++) {
+            uint4 t = lds128(r1_row + (c >> 3) * (kS_BlockBytes / 2) + (((c & 7) << 4) ^ r1_xor));
+            v[4 * c + 0] = t.x;
+            v[4 * c + 1] = t.y;
+            v[4 * c + 2] = t.z;
+            v[4 * c + 3] = t.w;
+        }
+        small_ct_row_stage<5, (LOGN > 6)>(v, tw_addr, q, two_q, zero);
+        small_ct_row_stage<4, true>(v, tw_addr, q, two_q, zero);
+        small_ct_row_stage<3, true>(v, tw_addr, q, two_q, zero);
+        small_ct_row_stage<2, true>(v, tw_addr, q, two_q, zero);
+        small_ct_row_stage<1, true>(v, tw_addr, q, two_q, zero);
+        small_ct_row_stage<0, true>(v, tw_addr, q, two_q, zero);
+#pragma unroll
+        for (int c = 0; c < 16; c++) {
+            uint32_t o[4];
+#pragma unroll
+            for (int e = 0; e < 4; e++) {
+                uint32_t r = v[4 * c + e];
+                r = min(r - two_q, r);
+                o[e] = min(r - q, r);
+            }
+            sts128(r1_row + (c >> 3) * (kS_BlockBytes / 2) + (((c & 7) << 4) ^ r1_xor), o[0], o[1],
+                   o[2], o[3]);
+        }
+        fence_proxy_async();
+        __syncwarp();
+        const uint64_t next = blk + stride;
+        if (j == 0) {
+            tma_store_3d(&out_lo, buf, 0, 0, (int) blk);
+            tma_store_3d(&out_hi, buf + kS_BlockBytes / 2, 0, 0, (int) blk);
+            tma_store_commit_and_wait_read();
+            if (next < prm.blocks) {
+                mbar_expect_tx(bar, kS_BlockBytes);
+                tma_load_3d(buf, &map_lo, bar, 0, 0, (int) next);
+                tma_load_3d(buf + kS_BlockBytes / 2, &map_hi, bar, 0, 0, (int) next);
+            }
+        }
+        __syncwarp();
     }
 }
 
@@ -191,10 +379,11 @@ int encode_tile_map(CUtensorMap *map, const int32_t *base, uint32_t rows, size_t
 
 template <int LOGN>
 static int small_set_attr() {
-    NTTB200_CUDA(cudaFuncSetAttribute(fused_gs_small_kernel<LOGN, false>,
-                                      cudaFuncAttributeMaxDynamicSharedMemorySize, kS_SmemBytes));
-    NTTB200_CUDA(cudaFuncSetAttribute(fused_gs_small_kernel<LOGN, true>,
-                                      cudaFuncAttributeMaxDynamicSharedMemorySize, kS_SmemBytes));
+    const auto attr = cudaFuncAttributeMaxDynamicSharedMemorySize;
+    NTTB200_CUDA(cudaFuncSetAttribute(fused_gs_small_kernel<LOGN, false, false>, attr, kS_SmemBytes));
+    NTTB200_CUDA(cudaFuncSetAttribute(fused_gs_small_kernel<LOGN, true, false>, attr, kS_SmemBytes));
+    NTTB200_CUDA(cudaFuncSetAttribute(fused_gs_small_kernel<LOGN, false, true>, attr, kS_SmemBytes));
+    NTTB200_CUDA(cudaFuncSetAttribute(fused_ct_small_kernel<LOGN>, attr, kS_SmemBytes));
     return NTTB200_OK;
 }
 
@@ -232,32 +421,62 @@ int small_prepare(nttb200_plan *p) {
     }
 }
 
+static uint32_t small_inv_mod_2_32(uint32_t q) {
+    uint32_t x = q;
+    for (int i = 0; i < 5; i++) x *= 2u - q * x;
+    return x;
+}
+
+// kind: 0 = GS, 1 = GS with ans_order store, 2 = GS of d_in (*) d_b scaled by N^-1, 3 = CT
 template <int LOGN>
-static void small_launch_t(bool permute, int grid, cudaStream_t st, const CUtensorMap &lo,
-                           const CUtensorMap &hi, const UniformTw &uni, const SmallParams &prm) {
-    if (permute) {
-        fused_gs_small_kernel<LOGN, true><<<grid, kS_Threads, kS_SmemBytes, st>>>(lo, hi, uni, prm);
-    } else {
-        fused_gs_small_kernel<LOGN, false><<<grid, kS_Threads, kS_SmemBytes, st>>>(lo, hi, uni, prm);
+static void small_launch_t(int kind, int grid, cudaStream_t st, const CUtensorMap &lo,
+                           const CUtensorMap &hi, const CUtensorMap &blo, const CUtensorMap &bhi,
+                           const UniformTw &uni, const SmallParams &prm) {
+    switch (kind) {
+        case 0:
+            fused_gs_small_kernel<LOGN, false, false><<<grid, kS_Threads, kS_SmemBytes, st>>>(
+                lo, hi, lo, hi, uni, prm);
+            break;
+        case 1:
+            fused_gs_small_kernel<LOGN, true, false><<<grid, kS_Threads, kS_SmemBytes, st>>>(
+                lo, hi, lo, hi, uni, prm);
+            break;
+        case 2:
+            fused_gs_small_kernel<LOGN, false, true><<<grid, kS_Threads, kS_SmemBytes, st>>>(
+                lo, hi, blo, bhi, uni, prm);
+            break;
+        default:
+            fused_ct_small_kernel<LOGN><<<grid, kS_Threads, kS_SmemBytes, st>>>(lo, hi, blo, bhi, uni,
+                                                                              prm);
+            break;
     }
 }
 
 // Handles the largest multiple of 2048 coefficients; *done_polys tells the caller how
 // many polynomials were transformed (the ragged tail goes through the generic pass).
-int launch_small_gs(nttb200_plan *p, const int32_t *d_in, int32_t *d_out, size_t batch,
-                    bool permute_out, cudaStream_t st, size_t *done_polys) {
+// d_b: second operand (kind 2) -- for kind 3 the output tensor maps are built on d_out.
+int launch_small(nttb200_plan *p, int kind, const int32_t *d_in, const int32_t *d_b, int32_t *d_out,
+                 size_t batch, cudaStream_t st, size_t *done_polys) {
     *done_polys = 0;
     if (p->logn < 9 || p->logn > 11 || !p->d_tw_r1) return NTTB200_ERR_UNSUPPORTED;
-    if (permute_out && p->logn != 11) return NTTB200_ERR_UNSUPPORTED;
+    if (kind == 1 && p->logn != 11) return NTTB200_ERR_UNSUPPORTED;
+    if (kind == 2 && !(p->q & 1u)) return NTTB200_ERR_UNSUPPORTED;
     const size_t per_block = (size_t) 2048 >> p->logn;
     const size_t blocks = batch / per_block;
     if (blocks == 0 || blocks > 0x7fffffffull || ((uintptr_t) d_in & 15u) ||
-        ((uintptr_t) d_out & 7u)) {
+        ((uintptr_t) d_out & 15u) || (d_b && ((uintptr_t) d_b & 15u))) {
         return NTTB200_ERR_UNSUPPORTED;
     }
-    CUtensorMap lo, hi;
+    CUtensorMap lo, hi, blo, bhi;
     if (encode_tile_map(&lo, d_in, 32, blocks) != NTTB200_OK ||
         encode_tile_map(&hi, d_in + 32, 32, blocks) != NTTB200_OK) {
+        return NTTB200_ERR_UNSUPPORTED;
+    }
+    blo = lo;
+    bhi = hi;
+    const int32_t *second = kind == 2 ? d_b : (kind == 3 ? d_out : nullptr);
+    if (second && (encode_tile_map(&blo, second, 32, blocks) != NTTB200_OK ||
+                   encode_tile_map(&bhi, second + 32, 32, blocks) != NTTB200_OK)) {
         return NTTB200_ERR_UNSUPPORTED;
     }
     SmallParams prm;
@@ -266,18 +485,31 @@ int launch_small_gs(nttb200_plan *p, const int32_t *d_in, int32_t *d_out, size_t
     prm.blocks = blocks;
     prm.q = p->q;
     prm.zero = 0;
+    prm.qinv = prm.scale = prm.scale_shoup = 0;
+    if (kind == 2) {
+        prm.qinv = small_inv_mod_2_32(p->q);
+        uint64_t sc = ((uint64_t) p->n_inv << 32) % p->q;
+        prm.scale = (uint32_t) sc;
+        prm.scale_shoup = (uint32_t) ((sc << 32) / p->q);
+    }
     uint64_t ctas = (blocks + kS_Warps - 1) / kS_Warps;
     int grid = (int) (ctas < (uint64_t) p->sm_count ? ctas : (uint64_t) p->sm_count);
     switch (p->logn) {
-        case 9: small_launch_t<9>(permute_out, grid, st, lo, hi, p->uni_gs, prm); break;
-        case 10: small_launch_t<10>(permute_out, grid, st, lo, hi, p->uni_gs, prm); break;
-        default: small_launch_t<11>(permute_out, grid, st, lo, hi, p->uni_gs, prm); break;
+        case 9: small_launch_t<9>(kind, grid, st, lo, hi, blo, bhi, p->uni_gs, prm); break;
+        case 10: small_launch_t<10>(kind, grid, st, lo, hi, blo, bhi, p->uni_gs, prm); break;
+        default: small_launch_t<11>(kind, grid, st, lo, hi, blo, bhi, p->uni_gs, prm); break;
     }
     g_launches.fetch_add(1, std::memory_order_relaxed);
     NTTB200_CUDA(cudaGetLastError());
-    p->last_path = "fused_gs_small_warp_tma";
+    p->last_path = kind == 3 ? "fused_ct_small_warp_tma"
+                             : (kind == 2 ? "fused_gs_small_warp_tma_dual" : "fused_gs_small_warp_tma");
     *done_polys = blocks * per_block;
     return NTTB200_OK;
+}
+
+int launch_small_gs(nttb200_plan *p, const int32_t *d_in, int32_t *d_out, size_t batch,
+                    bool permute_out, cudaStream_t st, size_t *done_polys) {
+    return launch_small(p, permute_out ? 1 : 0, d_in, nullptr, d_out, batch, st, done_polys);
 }
 
 }  // namespace nttb200

@@ -92,6 +92,8 @@ int launch_fused_gs(nttb200_plan *p, const int32_t *d_in, int32_t *d_out, size_t
 
 // warp-per-block kernel for N = 2^9..2^11 (kernels_small.cu)
 int small_prepare(nttb200_plan *p);
+int launch_small(nttb200_plan *p, int kind, const int32_t *d_in, const int32_t *d_b, int32_t *d_out,
+                 size_t batch, cudaStream_t st, size_t *done_polys);
 int launch_small_gs(nttb200_plan *p, const int32_t *d_in, int32_t *d_out, size_t batch,
                     bool permute_out, cudaStream_t st, size_t *done_polys);
 

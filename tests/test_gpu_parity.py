@@ -447,3 +447,33 @@ def test_rns_batches(lib, oracle_mod):
         pi.gs(d_a, d_a, batch)
         for l, q in enumerate(qs):
             assert np.array_equal(d_a.cpu().numpy()[:, l], oracle_mod.ntt_gs(a[:, l], inv_t[l], q))
+
+
+@pytest.mark.parametrize("logn", [9, 10, 11])
+def test_small_n_ct_and_polymul_fast_paths(lib, oracle_mod, logn):
+    """N = 512..2048: warp-per-block forward (CT) kernel and the product kernel
+    (pointwise + inverse + N^-1 in one launch), whole and ragged batches, q = 3329-like
+    small prime (12289 for N <= 2048 negacyclic needs 2N | q-1) and 29-bit q."""
+    n = 1 << logn
+    rng = np.random.default_rng(14000 + logn)
+    for q, g in ((Q29, 3), (12289, 11)):
+        fwd, inv = lib.negacyclic_tables(n, q, g)
+        for batch in (8, 9, 64):
+            a = rng.integers(0, q, (batch, n), dtype=np.int32)
+            b = rng.integers(0, q, (batch, n), dtype=np.int32)
+            a[0] = q - 1
+            d_a, d_b = dev(a), dev(b)
+            d_c = torch.empty_like(d_a)
+            with lib.Plan(logn, q, fwd) as pf, lib.Plan(logn, q, inv) as pi:
+                pf.ct(d_a, d_c, batch)
+                assert "ct_small" in pf.last_path, pf.last_path
+                assert np.array_equal(d_c.cpu().numpy(), oracle_mod.ntt_ct(a, fwd, q)), (logn, q, batch)
+                lib.polymul_negacyclic(pf, pi, d_a, d_b, d_c, batch)
+                if batch % (2048 >> logn) == 0:
+                    assert "dual" in pi.last_path, pi.last_path
+                prod = oracle_mod.pointwise(oracle_mod.ntt_ct(a, fwd, q), oracle_mod.ntt_ct(b, fwd, q), q)
+                want = oracle_mod.scale(oracle_mod.ntt_gs(prod, inv, q), oracle_mod.powmod(n, q - 2, q), q)
+                assert np.array_equal(d_c.cpu().numpy(), want), (logn, q, batch)
+                if logn <= 10:
+                    assert np.array_equal(want[1], oracle_mod.negacyclic_schoolbook(a[1], b[1], q))
+                assert np.array_equal(d_a.cpu().numpy(), a) and np.array_equal(d_b.cpu().numpy(), b)
