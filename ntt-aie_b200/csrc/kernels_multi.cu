@@ -33,17 +33,28 @@ constexpr int kM_SmemBytes = kM_Teams * kF_PolyBytes + 64 + 1024;
 
 __device__ __forceinline__ uint4 ldg128(const uint4 *p) { return __ldg(p); }
 
+// Where a team's twiddle slots come from: global memory (LDG, L1-resident across a
+// batch) or -- when every tile uses the same table (N = 4096) -- a shared-memory copy.
+struct TwGlobal {
+    const uint4 *p;
+    __device__ __forceinline__ uint4 slot(int s) const { return ldg128(p + s * 65); }
+};
+struct TwShared {
+    uint32_t addr;
+    __device__ __forceinline__ uint4 slot(int s) const { return lds128(addr + s * (65 * 16)); }
+};
+
 // One stage on the thread's 64 registers (pairs i, i + 2^S); the two (w, w') pairs of
 // blocks b, b+1 come as one uint4 from tw[slot * 65] (slot = 0,16,24,28,30,31 + b/2).
-template <int S, bool REDUCE>
-__device__ __forceinline__ void gs_stage_g(uint32_t (&v)[64], const uint4 *tw, uint32_t q,
+template <int S, bool REDUCE, class TW>
+__device__ __forceinline__ void gs_stage_t(uint32_t (&v)[64], const TW tw, uint32_t q,
                                            uint32_t two_q, uint32_t zero) {
     constexpr int kBlocks = 32 >> S;
     constexpr int kSlot0 = 32 - (kBlocks >= 2 ? kBlocks : 1);
     constexpr int kStride = 1 << S;
 #pragma unroll
     for (int b = 0; b < kBlocks; b += 2) {
-        uint4 t = ldg128(tw + (kSlot0 + b / 2) * kM_TwRow);
+        uint4 t = tw.slot(kSlot0 + b / 2);
 #pragma unroll
         for (int e = 0; e < kStride; e++) {
             int i0 = b * 2 * kStride + e;
@@ -61,15 +72,15 @@ __device__ __forceinline__ void gs_stage_g(uint32_t (&v)[64], const uint4 *tw, u
 
 
 // CT stage on the thread's 64 registers (pairs i, i + 2^S), same twiddle slots as GS
-template <int S, bool REDUCE_X>
-__device__ __forceinline__ void ct_stage_g(uint32_t (&v)[64], const uint4 *tw, uint32_t q,
+template <int S, bool REDUCE_X, class TW>
+__device__ __forceinline__ void ct_stage_t(uint32_t (&v)[64], const TW tw, uint32_t q,
                                            uint32_t two_q, uint32_t zero) {
     constexpr int kBlocks = 32 >> S;
     constexpr int kSlot0 = 32 - (kBlocks >= 2 ? kBlocks : 1);
     constexpr int kStride = 1 << S;
 #pragma unroll
     for (int b = 0; b < kBlocks; b += 2) {
-        uint4 t = ldg128(tw + (kSlot0 + b / 2) * kM_TwRow);
+        uint4 t = tw.slot(kSlot0 + b / 2);
 #pragma unroll
         for (int e = 0; e < kStride; e++) {
             int i0 = b * 2 * kStride + e;
@@ -84,6 +95,40 @@ __device__ __forceinline__ void ct_stage_g(uint32_t (&v)[64], const uint4 *tw, u
         }
     }
 }
+
+template <int S, bool REDUCE>
+__device__ __forceinline__ void gs_stage_g(uint32_t (&v)[64], const uint4 *tw, uint32_t q,
+                                           uint32_t two_q, uint32_t zero) {
+    gs_stage_t<S, REDUCE>(v, TwGlobal{tw}, q, two_q, zero);
+}
+template <int S, bool REDUCE_X>
+__device__ __forceinline__ void ct_stage_g(uint32_t (&v)[64], const uint4 *tw, uint32_t q,
+                                           uint32_t two_q, uint32_t zero) {
+    ct_stage_t<S, REDUCE_X>(v, TwGlobal{tw}, q, two_q, zero);
+}
+
+template <bool REDUCE0, class TW>
+__device__ __forceinline__ void gs_round(uint32_t (&v)[64], const TW tw, uint32_t q, uint32_t two_q,
+                                         uint32_t zero) {
+    gs_stage_t<0, REDUCE0>(v, tw, q, two_q, zero);
+    gs_stage_t<1, true>(v, tw, q, two_q, zero);
+    gs_stage_t<2, true>(v, tw, q, two_q, zero);
+    gs_stage_t<3, true>(v, tw, q, two_q, zero);
+    gs_stage_t<4, true>(v, tw, q, two_q, zero);
+    gs_stage_t<5, true>(v, tw, q, two_q, zero);
+}
+template <bool REDUCE_FIRST, class TW>
+__device__ __forceinline__ void ct_round(uint32_t (&v)[64], const TW tw, uint32_t q, uint32_t two_q,
+                                         uint32_t zero) {
+    ct_stage_t<5, REDUCE_FIRST>(v, tw, q, two_q, zero);
+    ct_stage_t<4, true>(v, tw, q, two_q, zero);
+    ct_stage_t<3, true>(v, tw, q, two_q, zero);
+    ct_stage_t<2, true>(v, tw, q, two_q, zero);
+    ct_stage_t<1, true>(v, tw, q, two_q, zero);
+    ct_stage_t<0, true>(v, tw, q, two_q, zero);
+}
+
+constexpr int kM_SmemBytesTw = kM_SmemBytes + kM_TwTile * 16;  // + one shared twiddle table
 
 struct TileParams {
     uint32_t *out;
@@ -112,7 +157,7 @@ struct RnsConsts {
 //   multiplied by `scale` (= N^-1 * 2^32 mod q for the inverse transform of a
 //   negacyclic product).  The network is linear, so scaling here instead of after the
 //   last column pass gives the same residues.
-template <bool DUAL, bool RNS>
+template <bool DUAL, bool RNS, bool SMEM_TW = false>
 __global__ void __launch_bounds__(kM_Threads, 1)
 tile_gs_kernel(const __grid_constant__ CUtensorMap map_lo, const __grid_constant__ CUtensorMap map_hi,
                const __grid_constant__ CUtensorMap map_b_lo,
@@ -131,6 +176,14 @@ tile_gs_kernel(const __grid_constant__ CUtensorMap map_lo, const __grid_constant
     uint32_t qinv = prm.qinv, scale = prm.scale, scale_shoup = prm.scale_shoup;
     const uint32_t zero = prm.zero;
 
+    // SMEM_TW (every tile uses the same table, N = 4096): one shared copy of the table
+    const uint32_t tws = bar_base + 64;
+    if (SMEM_TW) {
+        for (int i = tid; i < kM_TwTile; i += kM_Threads) {
+            uint4 x = __ldg(prm.tw_tile + i);
+            sts128(tws + i * 16, x.x, x.y, x.z, x.w);
+        }
+    }
     if (tid < kM_Teams) mbar_init(bar_base + tid * 8, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     __syncthreads();
@@ -210,13 +263,11 @@ tile_gs_kernel(const __grid_constant__ CUtensorMap map_lo, const __grid_constant
                 }
             }
         }
-        const uint4 *tw1 = tw + j;
-        gs_stage_g<0, DUAL>(v, tw1, q, two_q, zero);
-        gs_stage_g<1, true>(v, tw1, q, two_q, zero);
-        gs_stage_g<2, true>(v, tw1, q, two_q, zero);
-        gs_stage_g<3, true>(v, tw1, q, two_q, zero);
-        gs_stage_g<4, true>(v, tw1, q, two_q, zero);
-        gs_stage_g<5, true>(v, tw1, q, two_q, zero);
+        if (SMEM_TW) {
+            gs_round<DUAL>(v, TwShared{tws + j * 16}, q, two_q, zero);
+        } else {
+            gs_round<DUAL>(v, TwGlobal{tw + j}, q, two_q, zero);
+        }
 #pragma unroll
         for (int c = 0; c < 16; c++) {
             sts128(r1_row + (c >> 3) * (kF_PolyBytes / 2) + (((c & 7) << 4) ^ r1_xor), v[4 * c],
@@ -240,13 +291,11 @@ tile_gs_kernel(const __grid_constant__ CUtensorMap map_lo, const __grid_constant
                 tma_load_3d(buf + kF_PolyBytes / 2, &map_hi, bar, 0, 0, (int) tile_cur);
             }
         }
-        const uint4 *tw2 = tw + 64;
-        gs_stage_g<0, true>(v, tw2, q, two_q, zero);
-        gs_stage_g<1, true>(v, tw2, q, two_q, zero);
-        gs_stage_g<2, true>(v, tw2, q, two_q, zero);
-        gs_stage_g<3, true>(v, tw2, q, two_q, zero);
-        gs_stage_g<4, true>(v, tw2, q, two_q, zero);
-        gs_stage_g<5, true>(v, tw2, q, two_q, zero);
+        if (SMEM_TW) {
+            gs_round<true>(v, TwShared{tws + 64 * 16}, q, two_q, zero);
+        } else {
+            gs_round<true>(v, TwGlobal{tw + 64}, q, two_q, zero);
+        }
 
         uint32_t *dst = prm.out + (size_t) tile_store * 4096 + j;
 #pragma unroll
@@ -426,7 +475,7 @@ poly_gs_kernel(const __grid_constant__ CUtensorMap map_lo, const __grid_constant
 // Forward partner: CT stages 11..0 of every tile (stride 2048 -> 1).  Columns first
 // (uniform twiddles), exchange, rows (thread-private twiddles); the rows go back to the
 // team's buffer and leave through a TMA store.
-template <bool RNS>
+template <bool RNS, bool SMEM_TW = false>
 __global__ void __launch_bounds__(kM_Threads, 1)
 tile_ct_kernel(const __grid_constant__ CUtensorMap map_lo, const __grid_constant__ CUtensorMap map_hi,
                const __grid_constant__ CUtensorMap out_lo, const __grid_constant__ CUtensorMap out_hi,
@@ -443,6 +492,13 @@ tile_ct_kernel(const __grid_constant__ CUtensorMap map_lo, const __grid_constant
     uint32_t q = prm.q, two_q = 2u * prm.q;
     const uint32_t zero = prm.zero;
 
+    const uint32_t tws = bar_base + 64;
+    if (SMEM_TW) {
+        for (int i = tid; i < kM_TwTile; i += kM_Threads) {
+            uint4 x = __ldg(prm.tw_tile + i);
+            sts128(tws + i * 16, x.x, x.y, x.z, x.w);
+        }
+    }
     if (tid < kM_Teams) mbar_init(bar_base + tid * 8, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     __syncthreads();
@@ -489,13 +545,11 @@ tile_ct_kernel(const __grid_constant__ CUtensorMap map_lo, const __grid_constant
         for (int i = 0; i < 64; i++) {
             v[i] = lds32(r2_col + i * 128 + (r2_chunk ^ ((i & 7) << 4)));
         }
-        const uint4 *tw2 = tw + 64;
-        ct_stage_g<5, false>(v, tw2, q, two_q, zero);
-        ct_stage_g<4, true>(v, tw2, q, two_q, zero);
-        ct_stage_g<3, true>(v, tw2, q, two_q, zero);
-        ct_stage_g<2, true>(v, tw2, q, two_q, zero);
-        ct_stage_g<1, true>(v, tw2, q, two_q, zero);
-        ct_stage_g<0, true>(v, tw2, q, two_q, zero);
+        if (SMEM_TW) {
+            ct_round<false>(v, TwShared{tws + 64 * 16}, q, two_q, zero);
+        } else {
+            ct_round<false>(v, TwGlobal{tw + 64}, q, two_q, zero);
+        }
         // ---- exchange: column write, row read (thread j owns a[64j .. 64j+63])
 #pragma unroll
         for (int i = 0; i < 64; i++) {
@@ -513,13 +567,11 @@ tile_ct_kernel(const __grid_constant__ CUtensorMap map_lo, const __grid_constant
             v[4 * c + 3] = t.w;
         }
         // ---- rows: stages 5..0
-        const uint4 *tw1 = tw + j;
-        ct_stage_g<5, true>(v, tw1, q, two_q, zero);
-        ct_stage_g<4, true>(v, tw1, q, two_q, zero);
-        ct_stage_g<3, true>(v, tw1, q, two_q, zero);
-        ct_stage_g<2, true>(v, tw1, q, two_q, zero);
-        ct_stage_g<1, true>(v, tw1, q, two_q, zero);
-        ct_stage_g<0, true>(v, tw1, q, two_q, zero);
+        if (SMEM_TW) {
+            ct_round<true>(v, TwShared{tws + j * 16}, q, two_q, zero);
+        } else {
+            ct_round<true>(v, TwGlobal{tw + j}, q, two_q, zero);
+        }
         // ---- canonical rows back to the buffer, TMA store, then the next load
 #pragma unroll
         for (int c = 0; c < 16; c++) {
@@ -830,6 +882,9 @@ int multi_set_attrs() {
     NTTB200_CUDA(cudaFuncSetAttribute(tile_gs_kernel<true, true>, attr, kM_SmemBytes));
     NTTB200_CUDA(cudaFuncSetAttribute(tile_ct_kernel<false>, attr, kM_SmemBytes));
     NTTB200_CUDA(cudaFuncSetAttribute(tile_ct_kernel<true>, attr, kM_SmemBytes));
+    NTTB200_CUDA(cudaFuncSetAttribute(tile_gs_kernel<false, false, true>, attr, kM_SmemBytesTw));
+    NTTB200_CUDA(cudaFuncSetAttribute(tile_gs_kernel<true, false, true>, attr, kM_SmemBytesTw));
+    NTTB200_CUDA(cudaFuncSetAttribute(tile_ct_kernel<false, true>, attr, kM_SmemBytesTw));
     NTTB200_CUDA(cudaFuncSetAttribute(poly_ct_kernel<1>, attr, kM_SmemBytes));
     NTTB200_CUDA(cudaFuncSetAttribute(poly_ct_kernel<2>, attr, kM_SmemBytes));
     NTTB200_CUDA(cudaFuncSetAttribute(poly_ct_kernel<3>, attr, kM_SmemBytes));
@@ -1016,8 +1071,16 @@ static int launch_multi_gs_once(nttb200_plan *p, const int32_t *d_in, const int3
         uint64_t sc = ((uint64_t) p->n_inv << 32) % p->q;
         tp.scale = (uint32_t) sc;
         tp.scale_shoup = (uint32_t) ((sc << 32) / p->q);
-        tile_gs_kernel<true, false><<<grid, kM_Threads, kM_SmemBytes, st>>>(map_lo, map_hi, b_lo, b_hi,
-                                                                            tp, kNoRns);
+        if (tp.chunks == 1) {  // N = 4096: one table for every tile, kept in shared memory
+            tile_gs_kernel<true, false, true><<<grid, kM_Threads, kM_SmemBytesTw, st>>>(
+                map_lo, map_hi, b_lo, b_hi, tp, kNoRns);
+        } else {
+            tile_gs_kernel<true, false><<<grid, kM_Threads, kM_SmemBytes, st>>>(map_lo, map_hi, b_lo,
+                                                                                b_hi, tp, kNoRns);
+        }
+    } else if (tp.chunks == 1) {
+        tile_gs_kernel<false, false, true><<<grid, kM_Threads, kM_SmemBytesTw, st>>>(
+            map_lo, map_hi, map_lo, map_hi, tp, kNoRns);
     } else {
         tile_gs_kernel<false, false><<<grid, kM_Threads, kM_SmemBytes, st>>>(map_lo, map_hi, map_lo,
                                                                              map_hi, tp, kNoRns);
@@ -1200,8 +1263,13 @@ int launch_multi_ct(nttb200_plan *p, const int32_t *d_in, int32_t *d_out, size_t
         return NTTB200_ERR_UNSUPPORTED;
     }
     TileParams tp = tile_params(p, d_out, batch);
-    tile_ct_kernel<false><<<tile_grid(p, tiles), kM_Threads, kM_SmemBytes, st>>>(
-        in_lo, in_hi, out_lo, out_hi, tp, kNoRns);
+    if (tp.chunks == 1) {
+        tile_ct_kernel<false, true><<<tile_grid(p, tiles), kM_Threads, kM_SmemBytesTw, st>>>(
+            in_lo, in_hi, out_lo, out_hi, tp, kNoRns);
+    } else {
+        tile_ct_kernel<false><<<tile_grid(p, tiles), kM_Threads, kM_SmemBytes, st>>>(
+            in_lo, in_hi, out_lo, out_hi, tp, kNoRns);
+    }
     g_launches.fetch_add(1, std::memory_order_relaxed);
     NTTB200_CUDA(cudaGetLastError());
     p->last_path = "column_passes_ct + tile_tma_ct";
