@@ -143,6 +143,14 @@ NTTB200_API int nttb200_gs_stage_range_scatter(nttb200_plan *plan, int32_t *d_bu
 NTTB200_API int nttb200_gs_host(nttb200_plan *plan, const int32_t *h_in, int32_t *h_out,
                                 size_t batch, int stage_limit);
 
+/* Page-locked host buffers for nttb200_gs_host: the successor of the reference's
+ * host-only buffer objects `xrt::bo(device, size, XRT_BO_FLAGS_HOST_ONLY, ...)` +
+ * `.map<int32_t*>()` (src/test.cpp:115-134).  write_combined != 0 asks for
+ * write-combined memory (fast for the device to read, slow for the CPU to read back:
+ * use it for inputs only). */
+NTTB200_API int nttb200_host_alloc(void **ptr, size_t bytes, int write_combined);
+NTTB200_API int nttb200_host_free(void *ptr);
+
 /* ---- operators that make it a polynomial multiplier (new) ------------------- */
 
 /* c[i] = a[i]*b[i] mod q over count words. */

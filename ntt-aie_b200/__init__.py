@@ -12,6 +12,7 @@ the root-level shim: ``import ntt_aie_b200``.
 from .api import (  # noqa: F401
     NttError,
     Plan,
+    HostBuffer,
     RnsPlan,
     rns_polymul_negacyclic,
     ORDER_AIE_DEVICE,

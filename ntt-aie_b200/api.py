@@ -59,6 +59,8 @@ def load_library():
         "nttb200_gs_stage_range_scatter": (ctypes.c_int, [vp, vp, ctypes.c_int, ctypes.c_int,
                                                           ctypes.POINTER(vp), ctypes.c_int,
                                                           ctypes.c_int, vp]),
+        "nttb200_host_alloc": (ctypes.c_int, [ctypes.POINTER(vp), sz, ctypes.c_int]),
+        "nttb200_host_free": (ctypes.c_int, [vp]),
         "nttb200_pointwise": (ctypes.c_int, [vp, vp, vp, vp, sz, vp]),
         "nttb200_scale": (ctypes.c_int, [vp, vp, vp, sz, i32, vp]),
         "nttb200_polymul_negacyclic": (ctypes.c_int, [vp, vp, vp, vp, vp, sz, vp]),
@@ -87,7 +89,8 @@ def load_library():
 EXPORTED_SYMBOLS = (
     "nttb200_make_roots", "nttb200_make_bitrev_table", "nttb200_powmod", "nttb200_plan_create",
     "nttb200_plan_destroy", "nttb200_gs_batch", "nttb200_ct_batch", "nttb200_gs_stage_range",
-    "nttb200_gs_host", "nttb200_gs_stage_range_scatter", "nttb200_pointwise", "nttb200_scale", "nttb200_polymul_negacyclic",
+    "nttb200_gs_host", "nttb200_gs_stage_range_scatter", "nttb200_host_alloc", "nttb200_host_free",
+    "nttb200_pointwise", "nttb200_scale", "nttb200_polymul_negacyclic",
     "nttb200_rns_plan_create", "nttb200_rns_plan_destroy", "nttb200_rns_gs_batch",
     "nttb200_rns_ct_batch", "nttb200_rns_polymul_negacyclic",
     "nttb200_strerror", "nttb200_last_error", "nttb200_kernel_launches", "nttb200_plan_last_path",
@@ -136,6 +139,32 @@ def negacyclic_tables(n: int, q: int, g: int):
     psi = powmod(g, (q - 1) // (2 * n), q)
     psi_inv = powmod(psi, q - 2, q)
     return make_bitrev_table(n, q, psi), make_bitrev_table(n, q, psi_inv)
+
+
+class HostBuffer:
+    """Page-locked host memory from the library (successor of the reference's host-only
+    buffer objects, src/test.cpp:115-134).  `.array` is a numpy int32 view."""
+
+    def __init__(self, words: int, write_combined: bool = False):
+        self._lib = load_library()
+        p = ctypes.c_void_p()
+        _check(self._lib.nttb200_host_alloc(ctypes.byref(p), words * 4, 1 if write_combined else 0),
+               "host_alloc")
+        self.ptr = int(p.value)
+        self.words = words
+        self.array = np.ctypeslib.as_array((ctypes.c_int32 * words).from_address(self.ptr))
+
+    def free(self) -> None:
+        if getattr(self, "ptr", 0):
+            self.array = None
+            self._lib.nttb200_host_free(ctypes.c_void_p(self.ptr))
+            self.ptr = 0
+
+    def __del__(self):
+        try:
+            self.free()
+        except Exception:
+            pass
 
 
 # ------------------------------------------------------------------------- plan

@@ -368,6 +368,25 @@ int nttb200_gs_host(nttb200_plan *p, const int32_t *h_in, int32_t *h_out, size_t
     return NTTB200_OK;
 }
 
+int nttb200_host_alloc(void **ptr, size_t bytes, int write_combined) {
+    if (!ptr || bytes == 0) return NTTB200_ERR_INVALID_ARG;
+    *ptr = nullptr;
+    cudaError_t e = cudaHostAlloc(ptr, bytes,
+                                  cudaHostAllocPortable |
+                                      (write_combined ? cudaHostAllocWriteCombined : 0));
+    if (e == cudaErrorMemoryAllocation) {
+        cudaGetLastError();
+        return NTTB200_ERR_ALLOC;
+    }
+    return e == cudaSuccess ? NTTB200_OK : cuda_fail(e, "cudaHostAlloc");
+}
+
+int nttb200_host_free(void *ptr) {
+    if (!ptr) return NTTB200_OK;
+    cudaError_t e = cudaFreeHost(ptr);
+    return e == cudaSuccess ? NTTB200_OK : cuda_fail(e, "cudaFreeHost");
+}
+
 /* ---------------------------------------------------- multiplier operators */
 int nttb200_pointwise(nttb200_plan *p, const int32_t *d_a, const int32_t *d_b, int32_t *d_c,
                       size_t count, void *stream) {
