@@ -425,8 +425,15 @@ int nttb200_polymul_negacyclic(nttb200_plan *fwd, nttb200_plan *inv, const int32
         // N^-1 scaling in one pass over them
         NTTB200_CUDA(cudaMallocAsync(&tmp, sizeof(int32_t) * words * 2, st));
         int rc = launch_multi_ct(fwd, d_a, tmp, batch, st);
-        if (rc == NTTB200_OK) rc = launch_multi_ct(fwd, d_b, tmp + words, batch, st);
-        if (rc == NTTB200_OK) rc = launch_multi_gs_dual(inv, tmp, tmp + words, d_c, batch, st);
+        if (rc == NTTB200_OK && fwd->logn == 12 && inv->d_tw_r1 && !getenv("NTTB200_POLYMUL_DUAL")) {
+            // N = 4096: the pointwise product rides on the second forward transform (its
+            // operand load hides behind the row stages), the N^-1 on the inverse's store
+            rc = launch_multi_ct_mul(fwd, d_b, tmp, tmp + words, batch, st);
+            if (rc == NTTB200_OK) rc = launch_fused_gs_scaled(inv, tmp + words, d_c, batch, st);
+        } else {
+            if (rc == NTTB200_OK) rc = launch_multi_ct(fwd, d_b, tmp + words, batch, st);
+            if (rc == NTTB200_OK) rc = launch_multi_gs_dual(inv, tmp, tmp + words, d_c, batch, st);
+        }
         cudaError_t e = cudaFreeAsync(tmp, st);
         if (rc != NTTB200_ERR_UNSUPPORTED) {
             if (rc == NTTB200_OK && e != cudaSuccess) rc = cuda_fail(e, "cudaFreeAsync");

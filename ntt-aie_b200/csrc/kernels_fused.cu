@@ -110,9 +110,11 @@ struct FusedParams {
     uint32_t q;
     uint32_t zero;        // always 0 (see gs_bfly)
     uint32_t permute;     // ans_order on store (reference src/test.cpp:69-71,212-219)
+    uint32_t scale;       // SCALE: every output times this constant (Shoup pair) -- the
+    uint32_t scale_shoup; // N^-1 of an inverse transform, fused into the store
 };
 
-template <bool PERMUTE>
+template <bool PERMUTE, bool SCALE = false>
 __global__ void __launch_bounds__(kF_Threads, 1)
 fused_gs4096_kernel(const __grid_constant__ CUtensorMap map_lo,
                     const __grid_constant__ CUtensorMap map_hi,
@@ -223,7 +225,12 @@ fused_gs4096_kernel(const __grid_constant__ CUtensorMap map_lo,
                 blk = ((blk & 0x5) << 1) | ((blk & 0xA) >> 1);
                 row = (blk << 2) | (i & 3);
             }
-            dst[row * 64] = v[i];
+            if (SCALE) {
+                uint32_t r = shoup_mul_lazy(v[i], prm.scale, prm.scale_shoup, q);
+                dst[row * 64] = min(r - q, r);
+            } else {
+                dst[row * 64] = v[i];
+            }
         }
     }
 }
@@ -304,6 +311,8 @@ int fused_prepare(nttb200_plan *p) {
                                       cudaFuncAttributeMaxDynamicSharedMemorySize, kF_SmemBytes));
     NTTB200_CUDA(cudaFuncSetAttribute(fused_gs4096_kernel<true>,
                                       cudaFuncAttributeMaxDynamicSharedMemorySize, kF_SmemBytes));
+    NTTB200_CUDA(cudaFuncSetAttribute(fused_gs4096_kernel<false, true>,
+                                      cudaFuncAttributeMaxDynamicSharedMemorySize, kF_SmemBytes));
     return NTTB200_OK;
 }
 
@@ -312,8 +321,24 @@ void fused_release(nttb200_plan *p) {
     p->d_tw_r1 = nullptr;
 }
 
+static int launch_fused_impl(nttb200_plan *p, const int32_t *d_in, int32_t *d_out, size_t batch,
+                             bool permute_out, bool scaled, cudaStream_t st);
+
 int launch_fused_gs(nttb200_plan *p, const int32_t *d_in, int32_t *d_out, size_t batch,
                     bool permute_out, cudaStream_t st) {
+    return launch_fused_impl(p, d_in, d_out, batch, permute_out, false, st);
+}
+
+// golden network followed by a multiplication of every output by N^-1 * 2^32 mod q: the
+// inverse transform of a Montgomery-form pointwise product (nttb200_polymul_negacyclic)
+int launch_fused_gs_scaled(nttb200_plan *p, const int32_t *d_in, int32_t *d_out, size_t batch,
+                           cudaStream_t st) {
+    if (!(p->q & 1u)) return NTTB200_ERR_UNSUPPORTED;
+    return launch_fused_impl(p, d_in, d_out, batch, false, true, st);
+}
+
+static int launch_fused_impl(nttb200_plan *p, const int32_t *d_in, int32_t *d_out, size_t batch,
+                             bool permute_out, bool scaled, cudaStream_t st) {
     if (p->logn != 12 || !p->d_tw_r1) return NTTB200_ERR_UNSUPPORTED;
     if (batch == 0) return NTTB200_OK;
     if (batch > 0x7fffffffull || ((uintptr_t) d_in & 15u) || ((uintptr_t) d_out & 3u)) {
@@ -330,9 +355,18 @@ int launch_fused_gs(nttb200_plan *p, const int32_t *d_in, int32_t *d_out, size_t
     prm.q = p->q;
     prm.zero = 0;
     prm.permute = permute_out;
+    prm.scale = prm.scale_shoup = 0;
+    if (scaled) {
+        uint64_t sc = ((uint64_t) p->n_inv << 32) % p->q;
+        prm.scale = (uint32_t) sc;
+        prm.scale_shoup = (uint32_t) ((sc << 32) / p->q);
+    }
     uint64_t ctas = (batch + kF_Teams - 1) / kF_Teams;
     int grid = (int) (ctas < (uint64_t) p->sm_count ? ctas : (uint64_t) p->sm_count);
-    if (permute_out) {
+    if (scaled) {
+        fused_gs4096_kernel<false, true><<<grid, kF_Threads, kF_SmemBytes, st>>>(map_lo, map_hi,
+                                                                                 p->uni_gs, prm);
+    } else if (permute_out) {
         fused_gs4096_kernel<true><<<grid, kF_Threads, kF_SmemBytes, st>>>(map_lo, map_hi, p->uni_gs,
                                                                           prm);
     } else {
@@ -341,7 +375,7 @@ int launch_fused_gs(nttb200_plan *p, const int32_t *d_in, int32_t *d_out, size_t
     }
     g_launches.fetch_add(1, std::memory_order_relaxed);
     NTTB200_CUDA(cudaGetLastError());
-    p->last_path = "fused_gs4096_tma";
+    p->last_path = scaled ? "fused_gs4096_tma_scaled" : "fused_gs4096_tma";
     return NTTB200_OK;
 }
 

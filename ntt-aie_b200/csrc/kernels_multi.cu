@@ -475,11 +475,16 @@ poly_gs_kernel(const __grid_constant__ CUtensorMap map_lo, const __grid_constant
 // Forward partner: CT stages 11..0 of every tile (stride 2048 -> 1).  Columns first
 // (uniform twiddles), exchange, rows (thread-private twiddles); the rows go back to the
 // team's buffer and leave through a TMA store.
-template <bool RNS, bool SMEM_TW = false>
+// MULT: the transformed tile is multiplied point by point with the same tile of a third
+// buffer (an already transformed operand) before it is stored -- a Montgomery product
+// x*y*2^-32, canonical.  That operand's TMA load is issued as soon as the rows are in
+// registers and lands behind the six row stages, so it costs no waiting.
+template <bool RNS, bool SMEM_TW = false, bool MULT = false>
 __global__ void __launch_bounds__(kM_Threads, 1)
 tile_ct_kernel(const __grid_constant__ CUtensorMap map_lo, const __grid_constant__ CUtensorMap map_hi,
                const __grid_constant__ CUtensorMap out_lo, const __grid_constant__ CUtensorMap out_hi,
-               const TileParams prm, const __grid_constant__ RnsConsts rns) {
+               const TileParams prm, const __grid_constant__ RnsConsts rns,
+               const __grid_constant__ CUtensorMap mul_lo, const __grid_constant__ CUtensorMap mul_hi) {
     extern __shared__ uint8_t smem_raw[];
     const uint32_t data_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
     const uint32_t bar_base = data_base + kM_Teams * kF_PolyBytes;
@@ -566,20 +571,45 @@ tile_ct_kernel(const __grid_constant__ CUtensorMap map_lo, const __grid_constant
             v[4 * c + 2] = t.z;
             v[4 * c + 3] = t.w;
         }
+        if (MULT) {
+            // the buffer is idle during the row stages: fetch the other operand's tile
+            fence_proxy_async();
+            team_sync(team);
+            if (j == 0) {
+                mbar_expect_tx(bar, kF_PolyBytes);
+                tma_load_3d(buf, &mul_lo, bar, 0, 0, (int) tile_cur);
+                tma_load_3d(buf + kF_PolyBytes / 2, &mul_hi, bar, 0, 0, (int) tile_cur);
+            }
+        }
         // ---- rows: stages 5..0
         if (SMEM_TW) {
             ct_round<true>(v, TwShared{tws + j * 16}, q, two_q, zero);
         } else {
             ct_round<true>(v, TwGlobal{tw + j}, q, two_q, zero);
         }
+        if (MULT) {
+            mbar_wait(bar, parity);
+            parity ^= 1;
+        }
         // ---- canonical rows back to the buffer, TMA store, then the next load
 #pragma unroll
         for (int c = 0; c < 16; c++) {
             uint32_t o[4];
+            uint4 other = make_uint4(0, 0, 0, 0);
+            if (MULT) {
+                other = lds128(r1_row + (c >> 3) * (kF_PolyBytes / 2) + (((c & 7) << 4) ^ r1_xor));
+            }
+            const uint32_t ob[4] = {other.x, other.y, other.z, other.w};
 #pragma unroll
             for (int e = 0; e < 4; e++) {
                 uint32_t r = v[4 * c + e];
                 r = min(r - two_q, r);
+                if (MULT) {
+                    // r in [0, 2q), other operand canonical: x*y*2^-32 in (0, 2q)
+                    uint64_t prod = (uint64_t) r * ob[e];
+                    uint32_t m = (uint32_t) prod * prm.qinv;
+                    r = (uint32_t) (prod >> 32) - __umulhi(m, q) + q;
+                }
                 o[e] = min(r - q, r);
             }
             sts128(r1_row + (c >> 3) * (kF_PolyBytes / 2) + (((c & 7) << 4) ^ r1_xor), o[0], o[1],
@@ -885,6 +915,7 @@ int multi_set_attrs() {
     NTTB200_CUDA(cudaFuncSetAttribute(tile_gs_kernel<false, false, true>, attr, kM_SmemBytesTw));
     NTTB200_CUDA(cudaFuncSetAttribute(tile_gs_kernel<true, false, true>, attr, kM_SmemBytesTw));
     NTTB200_CUDA(cudaFuncSetAttribute(tile_ct_kernel<false, true>, attr, kM_SmemBytesTw));
+    NTTB200_CUDA(cudaFuncSetAttribute(tile_ct_kernel<false, true, true>, attr, kM_SmemBytesTw));
     NTTB200_CUDA(cudaFuncSetAttribute(poly_ct_kernel<1>, attr, kM_SmemBytes));
     NTTB200_CUDA(cudaFuncSetAttribute(poly_ct_kernel<2>, attr, kM_SmemBytes));
     NTTB200_CUDA(cudaFuncSetAttribute(poly_ct_kernel<3>, attr, kM_SmemBytes));
@@ -1218,7 +1249,18 @@ int launch_multi_gs_dual(nttb200_plan *p, const int32_t *d_a, const int32_t *d_b
 // CT tile pass
 int launch_multi_ct(nttb200_plan *p, const int32_t *d_in, int32_t *d_out, size_t batch,
                     cudaStream_t st) {
+    return launch_multi_ct_mul(p, d_in, nullptr, d_out, batch, st);
+}
+
+// d_mul != nullptr (N = 4096 only): out = CT(d_in) (*) d_mul as a Montgomery product
+// (x*y*2^-32 mod q, canonical) -- the pointwise product fused into the second forward
+// transform of a negacyclic multiplication
+int launch_multi_ct_mul(nttb200_plan *p, const int32_t *d_in, const int32_t *d_mul, int32_t *d_out,
+                        size_t batch, cudaStream_t st) {
     if (!multi_args_ok(p, d_in, d_out, batch)) return NTTB200_ERR_UNSUPPORTED;
+    if (d_mul && (p->logn != 12 || ((uintptr_t) d_mul & 15u) || !(p->q & 1u))) {
+        return NTTB200_ERR_UNSUPPORTED;
+    }
     if (batch == 0) return NTTB200_OK;
     const int logg = (int) p->logn - 12;
     if (logg >= 1 && logg <= 3 && poly_kernel_enabled()) {
@@ -1263,12 +1305,22 @@ int launch_multi_ct(nttb200_plan *p, const int32_t *d_in, int32_t *d_out, size_t
         return NTTB200_ERR_UNSUPPORTED;
     }
     TileParams tp = tile_params(p, d_out, batch);
+    CUtensorMap mul_lo, mul_hi;
+    if (d_mul) {
+        if (tile_maps(&mul_lo, &mul_hi, d_mul, (size_t) tiles) != NTTB200_OK) return NTTB200_ERR_UNSUPPORTED;
+        tp.qinv = inv_mod_2_32(p->q);
+    }
     if (tp.chunks == 1) {
-        tile_ct_kernel<false, true><<<tile_grid(p, tiles), kM_Threads, kM_SmemBytesTw, st>>>(
-            in_lo, in_hi, out_lo, out_hi, tp, kNoRns);
+        if (d_mul) {
+            tile_ct_kernel<false, true, true><<<tile_grid(p, tiles), kM_Threads, kM_SmemBytesTw, st>>>(
+                in_lo, in_hi, out_lo, out_hi, tp, kNoRns, mul_lo, mul_hi);
+        } else {
+            tile_ct_kernel<false, true><<<tile_grid(p, tiles), kM_Threads, kM_SmemBytesTw, st>>>(
+                in_lo, in_hi, out_lo, out_hi, tp, kNoRns, in_lo, in_hi);
+        }
     } else {
         tile_ct_kernel<false><<<tile_grid(p, tiles), kM_Threads, kM_SmemBytes, st>>>(
-            in_lo, in_hi, out_lo, out_hi, tp, kNoRns);
+            in_lo, in_hi, out_lo, out_hi, tp, kNoRns, in_lo, in_hi);
     }
     g_launches.fetch_add(1, std::memory_order_relaxed);
     NTTB200_CUDA(cudaGetLastError());
@@ -1309,7 +1361,8 @@ int rns_launch(int sm_count, int kind, const uint4 *d_tw_tile, const uint4 *h_po
                                                                             rc);
     } else if (kind == 1) {  // CT (output tensor maps on d_out)
         if (tile_maps(&b_lo, &b_hi, d_out, (size_t) tiles) != NTTB200_OK) return NTTB200_ERR_CUDA;
-        tile_ct_kernel<true><<<grid, kM_Threads, kM_SmemBytes, st>>>(a_lo, a_hi, b_lo, b_hi, tp, rc);
+        tile_ct_kernel<true><<<grid, kM_Threads, kM_SmemBytes, st>>>(a_lo, a_hi, b_lo, b_hi, tp, rc, a_lo,
+                                                                     a_hi);
     } else {                 // GS of the pointwise product, scaled
         if (tile_maps(&b_lo, &b_hi, d_b, (size_t) tiles) != NTTB200_OK) return NTTB200_ERR_CUDA;
         tile_gs_kernel<true, true><<<grid, kM_Threads, kM_SmemBytes, st>>>(a_lo, a_hi, b_lo, b_hi, tp,

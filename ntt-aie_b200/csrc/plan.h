@@ -113,6 +113,10 @@ uint32_t rns_inv_mod_2_32(uint32_t q);
 constexpr int kRnsTwTile = 32 * 65;  // uint4s per channel in d_tw_tile (kernels_multi.cu)
 int launch_multi_ct(nttb200_plan *p, const int32_t *d_in, int32_t *d_out, size_t batch,
                     cudaStream_t st);
+int launch_multi_ct_mul(nttb200_plan *p, const int32_t *d_in, const int32_t *d_mul, int32_t *d_out,
+                        size_t batch, cudaStream_t st);
+int launch_fused_gs_scaled(nttb200_plan *p, const int32_t *d_in, int32_t *d_out, size_t batch,
+                           cudaStream_t st);
 int launch_multi_gs_dual(nttb200_plan *p, const int32_t *d_a, const int32_t *d_b, int32_t *d_out,
                          size_t batch, cudaStream_t st);
 
