@@ -38,7 +38,8 @@ def build_library(verbose: bool = False, force: bool = False) -> str:
     os.makedirs(LIBDIR, exist_ok=True)
     hdrs = [h if os.path.isabs(h) else os.path.join(CSRC, h) for h in HEADERS]
     objs = []
-    for src in SOURCES:
+
+    def compile_one(src: str) -> str:
         s = os.path.join(CSRC, src)
         o = os.path.join(LIBDIR, src.replace(".cu", ".o"))
         if force or _stale(o, [s] + hdrs):
@@ -50,7 +51,11 @@ def build_library(verbose: bool = False, force: bool = False) -> str:
                 raise RuntimeError(f"nvcc failed on {src}")
             with open(o + ".ptxas.log", "w") as f:
                 f.write(res.stderr)
-        objs.append(o)
+        return o
+
+    from concurrent.futures import ThreadPoolExecutor
+    with ThreadPoolExecutor(max_workers=min(len(SOURCES), os.cpu_count() or 1)) as pool:
+        objs = list(pool.map(compile_one, SOURCES))
     if force or _stale(LIB, objs):
         cmd = [NVCC, "-shared", "-o", LIB] + objs + ARCH + ["-lcudart_static", "-lcuda", "-lpthread",
                                                           "-ldl", "-lrt"]
