@@ -638,6 +638,150 @@ tile_ct_kernel(const __grid_constant__ CUtensorMap map_lo, const __grid_constant
     // registers -- measured in the SASS.)
 }
 
+// N = 4096 forward transform with TWO buffers per team (6 teams per CTA): the output of
+// tile k leaves buffer k&1 through a TMA store while tile k+1 is already being worked
+// on in the other buffer and tile k+2's load is queued behind the store -- the dead
+// time of tile_ct_kernel (store drain + load latency after every tile) disappears.
+constexpr int kD_Teams = 6;
+constexpr int kD_Threads = kD_Teams * kF_Team;
+constexpr int kD_SmemBytes = kD_Teams * 2 * kF_PolyBytes + kM_TwTile * 16 + 128 + 1024;
+
+template <bool MULT>
+__global__ void __launch_bounds__(kD_Threads, 1)
+tile_ct_db_kernel(const __grid_constant__ CUtensorMap map_lo, const __grid_constant__ CUtensorMap map_hi,
+                  const __grid_constant__ CUtensorMap out_lo, const __grid_constant__ CUtensorMap out_hi,
+                  const __grid_constant__ CUtensorMap mul_lo, const __grid_constant__ CUtensorMap mul_hi,
+                  const TileParams prm) {
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t data_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    const uint32_t bar_base = data_base + kD_Teams * 2 * kF_PolyBytes;   // 2 mbarriers per team
+    const uint32_t tws = bar_base + 128;
+    const int tid = threadIdx.x;
+    const int team = __shfl_sync(0xffffffffu, tid >> 6, 0);
+    const int j = tid & 63;
+    const uint32_t q = prm.q, two_q = 2u * prm.q, zero = prm.zero;
+
+    for (int i = tid; i < kM_TwTile; i += kD_Threads) {
+        uint4 x = __ldg(prm.tw_tile + i);
+        sts128(tws + i * 16, x.x, x.y, x.z, x.w);
+    }
+    if (tid < kD_Teams * 2) mbar_init(bar_base + tid * 8, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    __syncthreads();
+
+    const uint32_t total = prm.batch;  // chunks == 1
+    const uint32_t stride = gridDim.x * kD_Teams;
+    uint32_t tile = blockIdx.x * kD_Teams + team;
+    const uint32_t buf0 = data_base + team * 2 * kF_PolyBytes;
+    const uint32_t bar0 = bar_base + team * 16;
+    uint32_t parity0 = 0, parity1 = 0;
+    if (j == 0 && tile < total) {
+        mbar_expect_tx(bar0, kF_PolyBytes);
+        tma_load_3d(buf0, &map_lo, bar0, 0, 0, (int) tile);
+        tma_load_3d(buf0 + kF_PolyBytes / 2, &map_hi, bar0, 0, 0, (int) tile);
+    }
+    const uint32_t r1_off = j * 128;
+    const uint32_t r1_xor = (j & 7) << 4;
+    const uint32_t r2_off = (j >> 5) * (kF_PolyBytes / 2) + (j & 3) * 4;
+    const uint32_t r2_chunk = ((j & 31) >> 2) << 4;
+
+    for (uint32_t k = 0; tile < total; tile += stride, k++) {
+        const uint32_t cur = k & 1;
+        const uint32_t buf = buf0 + cur * kF_PolyBytes;
+        const uint32_t bar = bar0 + cur * 8;
+        const uint32_t next = tile + stride;
+        if (j == 0) {
+            // the other buffer held the previous tile's output: once the TMA store has
+            // read it, queue the next tile's load there
+            asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+            if (next < total) {
+                const uint32_t nbuf = buf0 + (cur ^ 1) * kF_PolyBytes, nbar = bar0 + (cur ^ 1) * 8;
+                mbar_expect_tx(nbar, kF_PolyBytes);
+                tma_load_3d(nbuf, &map_lo, nbar, 0, 0, (int) next);
+                tma_load_3d(nbuf + kF_PolyBytes / 2, &map_hi, nbar, 0, 0, (int) next);
+            }
+        }
+        uint32_t v[64];
+        if (cur == 0) {
+            mbar_wait(bar, parity0);
+            parity0 ^= 1;
+        } else {
+            mbar_wait(bar, parity1);
+            parity1 ^= 1;
+        }
+        const uint32_t r2_col = buf + r2_off, r1_row = buf + r1_off;
+#pragma unroll
+        for (int i = 0; i < 64; i++) {
+            v[i] = lds32(r2_col + i * 128 + (r2_chunk ^ ((i & 7) << 4)));
+        }
+        ct_round<false>(v, TwShared{tws + 64 * 16}, q, two_q, zero);
+#pragma unroll
+        for (int i = 0; i < 64; i++) {
+            asm volatile("st.shared.u32 [%0], %1;" ::"r"(r2_col + i * 128 + (r2_chunk ^ ((i & 7) << 4))),
+                         "r"(v[i])
+                         : "memory");
+        }
+        team_sync(team);
+#pragma unroll
+        for (int c = 0; c < 16; c++) {
+            uint4 t = lds128(r1_row + (c >> 3) * (kF_PolyBytes / 2) + (((c & 7) << 4) ^ r1_xor));
+            v[4 * c + 0] = t.x;
+            v[4 * c + 1] = t.y;
+            v[4 * c + 2] = t.z;
+            v[4 * c + 3] = t.w;
+        }
+        if (MULT) {
+            fence_proxy_async();
+            team_sync(team);
+            if (j == 0) {
+                mbar_expect_tx(bar, kF_PolyBytes);
+                tma_load_3d(buf, &mul_lo, bar, 0, 0, (int) tile);
+                tma_load_3d(buf + kF_PolyBytes / 2, &mul_hi, bar, 0, 0, (int) tile);
+            }
+        }
+        ct_round<true>(v, TwShared{tws + j * 16}, q, two_q, zero);
+        if (MULT) {
+            if (cur == 0) {
+                mbar_wait(bar, parity0);
+                parity0 ^= 1;
+            } else {
+                mbar_wait(bar, parity1);
+                parity1 ^= 1;
+            }
+        }
+#pragma unroll
+        for (int c = 0; c < 16; c++) {
+            uint32_t o[4];
+            uint4 other = make_uint4(0, 0, 0, 0);
+            if (MULT) {
+                other = lds128(r1_row + (c >> 3) * (kF_PolyBytes / 2) + (((c & 7) << 4) ^ r1_xor));
+            }
+            const uint32_t ob[4] = {other.x, other.y, other.z, other.w};
+#pragma unroll
+            for (int e = 0; e < 4; e++) {
+                uint32_t r = v[4 * c + e];
+                r = min(r - two_q, r);
+                if (MULT) {
+                    uint64_t prod = (uint64_t) r * ob[e];
+                    uint32_t m = (uint32_t) prod * prm.qinv;
+                    r = (uint32_t) (prod >> 32) - __umulhi(m, q) + q;
+                }
+                o[e] = min(r - q, r);
+            }
+            sts128(r1_row + (c >> 3) * (kF_PolyBytes / 2) + (((c & 7) << 4) ^ r1_xor), o[0], o[1],
+                   o[2], o[3]);
+        }
+        fence_proxy_async();
+        team_sync(team);
+        if (j == 0) {
+            tma_store_3d(&out_lo, buf, 0, 0, (int) tile);
+            tma_store_3d(&out_hi, buf + kF_PolyBytes / 2, 0, 0, (int) tile);
+            asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+        }
+    }
+    if (j == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+}
+
 // Forward partner of poly_gs_kernel: N = 2^13..2^15 in one pass.  The cross-tile stages
 // come FIRST in the CT order (largest strides): once the G tiles of a polynomial have
 // landed, every thread gathers its slice of rows from all G tile buffers, runs stages
@@ -916,6 +1060,8 @@ int multi_set_attrs() {
     NTTB200_CUDA(cudaFuncSetAttribute(tile_gs_kernel<true, false, true>, attr, kM_SmemBytesTw));
     NTTB200_CUDA(cudaFuncSetAttribute(tile_ct_kernel<false, true>, attr, kM_SmemBytesTw));
     NTTB200_CUDA(cudaFuncSetAttribute(tile_ct_kernel<false, true, true>, attr, kM_SmemBytesTw));
+    NTTB200_CUDA(cudaFuncSetAttribute(tile_ct_db_kernel<false>, attr, kD_SmemBytes));
+    NTTB200_CUDA(cudaFuncSetAttribute(tile_ct_db_kernel<true>, attr, kD_SmemBytes));
     NTTB200_CUDA(cudaFuncSetAttribute(poly_ct_kernel<1>, attr, kM_SmemBytes));
     NTTB200_CUDA(cudaFuncSetAttribute(poly_ct_kernel<2>, attr, kM_SmemBytes));
     NTTB200_CUDA(cudaFuncSetAttribute(poly_ct_kernel<3>, attr, kM_SmemBytes));
@@ -1310,7 +1456,18 @@ int launch_multi_ct_mul(nttb200_plan *p, const int32_t *d_in, const int32_t *d_m
         if (tile_maps(&mul_lo, &mul_hi, d_mul, (size_t) tiles) != NTTB200_OK) return NTTB200_ERR_UNSUPPORTED;
         tp.qinv = inv_mod_2_32(p->q);
     }
-    if (tp.chunks == 1) {
+    static const bool use_db = getenv("NTTB200_CT_SINGLE_BUFFER") == nullptr;
+    if (tp.chunks == 1 && use_db) {
+        uint64_t ctas = (tiles + kD_Teams - 1) / kD_Teams;
+        int grid = (int) (ctas < (uint64_t) p->sm_count ? ctas : (uint64_t) p->sm_count);
+        if (d_mul) {
+            tile_ct_db_kernel<true><<<grid, kD_Threads, kD_SmemBytes, st>>>(in_lo, in_hi, out_lo, out_hi,
+                                                                           mul_lo, mul_hi, tp);
+        } else {
+            tile_ct_db_kernel<false><<<grid, kD_Threads, kD_SmemBytes, st>>>(in_lo, in_hi, out_lo, out_hi,
+                                                                            in_lo, in_hi, tp);
+        }
+    } else if (tp.chunks == 1) {
         if (d_mul) {
             tile_ct_kernel<false, true, true><<<tile_grid(p, tiles), kM_Threads, kM_SmemBytesTw, st>>>(
                 in_lo, in_hi, out_lo, out_hi, tp, kNoRns, mul_lo, mul_hi);
@@ -1324,7 +1481,8 @@ int launch_multi_ct_mul(nttb200_plan *p, const int32_t *d_in, const int32_t *d_m
     }
     g_launches.fetch_add(1, std::memory_order_relaxed);
     NTTB200_CUDA(cudaGetLastError());
-    p->last_path = "column_passes_ct + tile_tma_ct";
+    p->last_path = p->logn == 12 ? (d_mul ? "tile_tma_ct_mul" : "tile_tma_ct")
+                                 : "column_passes_ct + tile_tma_ct";
     return NTTB200_OK;
 }
 
