@@ -157,7 +157,12 @@ struct RnsConsts {
 //   multiplied by `scale` (= N^-1 * 2^32 mod q for the inverse transform of a
 //   negacyclic product).  The network is linear, so scaling here instead of after the
 //   last column pass gives the same residues.
-template <bool DUAL, bool RNS, bool SMEM_TW = false>
+// TWMODE: where the twiddles come from.  0 = global memory (LDG; any workload),
+// 1 = one shared-memory table for the whole launch (every tile at position 0: N = 4096),
+// 2 = shared-memory table per SEGMENT: the CTA's range of position-major tiles is cut
+//     at position changes, the table of the segment's position is staged between two
+//     __syncthreads (batched large-N and RNS workloads, where a segment is long).
+template <bool DUAL, bool RNS, int TWMODE = 0>
 __global__ void __launch_bounds__(kM_Threads, 1)
 tile_gs_kernel(const __grid_constant__ CUtensorMap map_lo, const __grid_constant__ CUtensorMap map_hi,
                const __grid_constant__ CUtensorMap map_b_lo,
@@ -176,9 +181,8 @@ tile_gs_kernel(const __grid_constant__ CUtensorMap map_lo, const __grid_constant
     uint32_t qinv = prm.qinv, scale = prm.scale, scale_shoup = prm.scale_shoup;
     const uint32_t zero = prm.zero;
 
-    // SMEM_TW (every tile uses the same table, N = 4096): one shared copy of the table
     const uint32_t tws = bar_base + 64;
-    if (SMEM_TW) {
+    if (TWMODE == 1) {
         for (int i = tid; i < kM_TwTile; i += kM_Threads) {
             uint4 x = __ldg(prm.tw_tile + i);
             sts128(tws + i * 16, x.x, x.y, x.z, x.w);
@@ -198,7 +202,6 @@ tile_gs_kernel(const __grid_constant__ CUtensorMap map_lo, const __grid_constant
     const uint32_t buf = data_base + team * kF_PolyBytes;
     const uint32_t bar = bar_base + team * 8;
     uint32_t parity = 0;
-    uint32_t u = u_begin + team;
 
     auto tile_of = [&](uint32_t uu, uint32_t &c) -> uint32_t {
         c = uu / prm.batch;
@@ -206,8 +209,31 @@ tile_gs_kernel(const __grid_constant__ CUtensorMap map_lo, const __grid_constant
         return poly * prm.chunks + c;  // tile index in memory
     };
 
+    const uint32_t r1_row = buf + j * 128;
+    const uint32_t r1_xor = (j & 7) << 4;
+    const uint32_t r2_col = buf + (j >> 5) * (kF_PolyBytes / 2) + (j & 3) * 4;
+    const uint32_t r2_chunk = ((j & 31) >> 2) << 4;
+
+    // segments of constant tile position (TWMODE 2); otherwise the whole range at once
+    const uint32_t c_first = TWMODE == 2 ? u_begin / prm.batch : 0;
+    const uint32_t c_last = (TWMODE == 2 && u_end > u_begin) ? (u_end - 1) / prm.batch : c_first;
+    for (uint32_t cs = c_first; cs <= c_last && u_begin < u_end; cs++) {
+    uint32_t seg_begin = u_begin, seg_end = u_end;
+    if (TWMODE == 2) {
+        const uint32_t lo = cs * prm.batch, hi = lo + prm.batch;
+        seg_begin = u_begin > lo ? u_begin : lo;
+        seg_end = u_end < hi ? u_end : hi;
+        __syncthreads();  // every team is done with the previous position's table
+        const uint4 *src = prm.tw_tile + (size_t) cs * kM_TwTile;
+        for (int i = tid; i < kM_TwTile; i += kM_Threads) {
+            uint4 x = __ldg(src + i);
+            sts128(tws + i * 16, x.x, x.y, x.z, x.w);
+        }
+        __syncthreads();
+    }
+    uint32_t u = seg_begin + team;
     uint32_t c_cur = 0, tile_cur = 0;
-    if (u < u_end) {
+    if (u < seg_end) {
         tile_cur = tile_of(u, c_cur);
         if (j == 0) {
             mbar_expect_tx(bar, kF_PolyBytes);
@@ -215,12 +241,8 @@ tile_gs_kernel(const __grid_constant__ CUtensorMap map_lo, const __grid_constant
             tma_load_3d(buf + kF_PolyBytes / 2, &map_hi, bar, 0, 0, (int) tile_cur);
         }
     }
-    const uint32_t r1_row = buf + j * 128;
-    const uint32_t r1_xor = (j & 7) << 4;
-    const uint32_t r2_col = buf + (j >> 5) * (kF_PolyBytes / 2) + (j & 3) * 4;
-    const uint32_t r2_chunk = ((j & 31) >> 2) << 4;
 
-    for (; u < u_end; u += kM_Teams) {
+    for (; u < seg_end; u += kM_Teams) {
         uint32_t v[64];
         const uint4 *tw = prm.tw_tile + (size_t) c_cur * kM_TwTile;
         if (RNS) {
@@ -263,7 +285,7 @@ tile_gs_kernel(const __grid_constant__ CUtensorMap map_lo, const __grid_constant
                 }
             }
         }
-        if (SMEM_TW) {
+        if (TWMODE != 0) {
             gs_round<DUAL>(v, TwShared{tws + j * 16}, q, two_q, zero);
         } else {
             gs_round<DUAL>(v, TwGlobal{tw + j}, q, two_q, zero);
@@ -283,7 +305,7 @@ tile_gs_kernel(const __grid_constant__ CUtensorMap map_lo, const __grid_constant
 
         const uint32_t tile_store = tile_cur;
         const uint32_t next = u + kM_Teams;
-        if (next < u_end) {
+        if (next < seg_end) {
             tile_cur = tile_of(next, c_cur);
             if (j == 0) {
                 mbar_expect_tx(bar, kF_PolyBytes);
@@ -291,7 +313,7 @@ tile_gs_kernel(const __grid_constant__ CUtensorMap map_lo, const __grid_constant
                 tma_load_3d(buf + kF_PolyBytes / 2, &map_hi, bar, 0, 0, (int) tile_cur);
             }
         }
-        if (SMEM_TW) {
+        if (TWMODE != 0) {
             gs_round<true>(v, TwShared{tws + 64 * 16}, q, two_q, zero);
         } else {
             gs_round<true>(v, TwGlobal{tw + 64}, q, two_q, zero);
@@ -304,6 +326,7 @@ tile_gs_kernel(const __grid_constant__ CUtensorMap map_lo, const __grid_constant
             dst[i * 64] = min(r - q, r);
         }
     }
+    }  // segments
 }
 
 // N = 2^13 .. 2^15 in ONE pass: the G = N/4096 tiles of a polynomial are taken by G
@@ -1056,8 +1079,12 @@ int multi_set_attrs() {
     NTTB200_CUDA(cudaFuncSetAttribute(tile_gs_kernel<true, true>, attr, kM_SmemBytes));
     NTTB200_CUDA(cudaFuncSetAttribute(tile_ct_kernel<false>, attr, kM_SmemBytes));
     NTTB200_CUDA(cudaFuncSetAttribute(tile_ct_kernel<true>, attr, kM_SmemBytes));
-    NTTB200_CUDA(cudaFuncSetAttribute(tile_gs_kernel<false, false, true>, attr, kM_SmemBytesTw));
-    NTTB200_CUDA(cudaFuncSetAttribute(tile_gs_kernel<true, false, true>, attr, kM_SmemBytesTw));
+    NTTB200_CUDA(cudaFuncSetAttribute(tile_gs_kernel<false, false, 1>, attr, kM_SmemBytesTw));
+    NTTB200_CUDA(cudaFuncSetAttribute(tile_gs_kernel<false, false, 2>, attr, kM_SmemBytesTw));
+    NTTB200_CUDA(cudaFuncSetAttribute(tile_gs_kernel<true, false, 2>, attr, kM_SmemBytesTw));
+    NTTB200_CUDA(cudaFuncSetAttribute(tile_gs_kernel<false, true, 2>, attr, kM_SmemBytesTw));
+    NTTB200_CUDA(cudaFuncSetAttribute(tile_gs_kernel<true, true, 2>, attr, kM_SmemBytesTw));
+    NTTB200_CUDA(cudaFuncSetAttribute(tile_gs_kernel<true, false, 1>, attr, kM_SmemBytesTw));
     NTTB200_CUDA(cudaFuncSetAttribute(tile_ct_kernel<false, true>, attr, kM_SmemBytesTw));
     NTTB200_CUDA(cudaFuncSetAttribute(tile_ct_kernel<false, true, true>, attr, kM_SmemBytesTw));
     NTTB200_CUDA(cudaFuncSetAttribute(tile_ct_db_kernel<false>, attr, kD_SmemBytes));
@@ -1230,6 +1257,12 @@ static int launch_poly_gs(nttb200_plan *p, const int32_t *d_in, const int32_t *d
     return NTTB200_OK;
 }
 
+// long same-position runs (batched workloads): stage each position's table in shared memory
+static bool seg_tables(size_t batch) {
+    static const bool off = getenv("NTTB200_NO_SEG_TABLES") != nullptr;
+    return !off && batch >= 64;
+}
+
 // d_b == nullptr: plain transform of d_in.  Otherwise the input is d_in (*) d_b and the
 // output is scaled by N^-1 (inverse transform of a negacyclic product).
 static int launch_multi_gs_once(nttb200_plan *p, const int32_t *d_in, const int32_t *d_b,
@@ -1249,14 +1282,20 @@ static int launch_multi_gs_once(nttb200_plan *p, const int32_t *d_in, const int3
         tp.scale = (uint32_t) sc;
         tp.scale_shoup = (uint32_t) ((sc << 32) / p->q);
         if (tp.chunks == 1) {  // N = 4096: one table for every tile, kept in shared memory
-            tile_gs_kernel<true, false, true><<<grid, kM_Threads, kM_SmemBytesTw, st>>>(
+            tile_gs_kernel<true, false, 1><<<grid, kM_Threads, kM_SmemBytesTw, st>>>(
+                map_lo, map_hi, b_lo, b_hi, tp, kNoRns);
+        } else if (seg_tables(batch)) {
+            tile_gs_kernel<true, false, 2><<<grid, kM_Threads, kM_SmemBytesTw, st>>>(
                 map_lo, map_hi, b_lo, b_hi, tp, kNoRns);
         } else {
             tile_gs_kernel<true, false><<<grid, kM_Threads, kM_SmemBytes, st>>>(map_lo, map_hi, b_lo,
                                                                                 b_hi, tp, kNoRns);
         }
     } else if (tp.chunks == 1) {
-        tile_gs_kernel<false, false, true><<<grid, kM_Threads, kM_SmemBytesTw, st>>>(
+        tile_gs_kernel<false, false, 1><<<grid, kM_Threads, kM_SmemBytesTw, st>>>(
+            map_lo, map_hi, map_lo, map_hi, tp, kNoRns);
+    } else if (seg_tables(batch)) {
+        tile_gs_kernel<false, false, 2><<<grid, kM_Threads, kM_SmemBytesTw, st>>>(
             map_lo, map_hi, map_lo, map_hi, tp, kNoRns);
     } else {
         tile_gs_kernel<false, false><<<grid, kM_Threads, kM_SmemBytes, st>>>(map_lo, map_hi, map_lo,
@@ -1515,16 +1554,26 @@ int rns_launch(int sm_count, int kind, const uint4 *d_tw_tile, const uint4 *h_po
     CUtensorMap a_lo, a_hi, b_lo, b_hi;
     if (tile_maps(&a_lo, &a_hi, d_a, (size_t) tiles) != NTTB200_OK) return NTTB200_ERR_CUDA;
     if (kind == 0) {         // GS
-        tile_gs_kernel<false, true><<<grid, kM_Threads, kM_SmemBytes, st>>>(a_lo, a_hi, a_lo, a_hi, tp,
-                                                                            rc);
+        if (seg_tables(batch)) {
+            tile_gs_kernel<false, true, 2><<<grid, kM_Threads, kM_SmemBytesTw, st>>>(a_lo, a_hi, a_lo,
+                                                                                    a_hi, tp, rc);
+        } else {
+            tile_gs_kernel<false, true><<<grid, kM_Threads, kM_SmemBytes, st>>>(a_lo, a_hi, a_lo, a_hi,
+                                                                                tp, rc);
+        }
     } else if (kind == 1) {  // CT (output tensor maps on d_out)
         if (tile_maps(&b_lo, &b_hi, d_out, (size_t) tiles) != NTTB200_OK) return NTTB200_ERR_CUDA;
         tile_ct_kernel<true><<<grid, kM_Threads, kM_SmemBytes, st>>>(a_lo, a_hi, b_lo, b_hi, tp, rc, a_lo,
                                                                      a_hi);
     } else {                 // GS of the pointwise product, scaled
         if (tile_maps(&b_lo, &b_hi, d_b, (size_t) tiles) != NTTB200_OK) return NTTB200_ERR_CUDA;
-        tile_gs_kernel<true, true><<<grid, kM_Threads, kM_SmemBytes, st>>>(a_lo, a_hi, b_lo, b_hi, tp,
-                                                                           rc);
+        if (seg_tables(batch)) {
+            tile_gs_kernel<true, true, 2><<<grid, kM_Threads, kM_SmemBytesTw, st>>>(a_lo, a_hi, b_lo,
+                                                                                   b_hi, tp, rc);
+        } else {
+            tile_gs_kernel<true, true><<<grid, kM_Threads, kM_SmemBytes, st>>>(a_lo, a_hi, b_lo, b_hi,
+                                                                               tp, rc);
+        }
     }
     g_launches.fetch_add(1, std::memory_order_relaxed);
     NTTB200_CUDA(cudaGetLastError());

@@ -477,3 +477,28 @@ def test_small_n_ct_and_polymul_fast_paths(lib, oracle_mod, logn):
                 if logn <= 10:
                     assert np.array_equal(want[1], oracle_mod.negacyclic_schoolbook(a[1], b[1], q))
                 assert np.array_equal(d_a.cpu().numpy(), a) and np.array_equal(d_b.cpu().numpy(), b)
+
+
+def test_segmented_table_path(lib, oracle_mod):
+    """Batches >= 64 of N >= 2^16 (and RNS batches) stage each tile position's twiddle
+    table in shared memory per segment of the CTA's work range: whole-batch parity with
+    a ragged batch that makes ranges straddle position changes."""
+    rng = np.random.default_rng(15000)
+    for logn, batch in ((16, 70), (17, 65)):
+        n = 1 << logn
+        table = rng.integers(0, Q29, n, dtype=np.int32)
+        a = rng.integers(0, Q29, (batch, n), dtype=np.int32)
+        out, path = run_gs(lib, a, table, Q29)
+        assert "tile" in path
+        assert np.array_equal(out, oracle_mod.ntt_gs(a, table, Q29)), logn
+    n, limbs, batch = 4096, 3, 67
+    qs = _ntt_primes(limbs)
+    tabs = [rng.integers(0, q, n, dtype=np.int32) for q in qs]
+    a = np.stack([np.stack([rng.integers(0, q, n, dtype=np.int32) for q in qs]) for _ in range(batch)])
+    d_a = dev(a)
+    d_o = torch.empty_like(d_a)
+    with lib.RnsPlan(qs, tabs) as rp:
+        rp.gs(d_a, d_o, batch)
+    got = d_o.cpu().numpy()
+    for l, q in enumerate(qs):
+        assert np.array_equal(got[:, l], oracle_mod.ntt_gs(a[:, l], tabs[l], q)), l
