@@ -441,7 +441,7 @@ int nttb200_polymul_negacyclic(nttb200_plan *fwd, nttb200_plan *inv, const int32
         }
         tmp = nullptr;  // fall through to the generic pipeline (nothing was written to d_c)
     }
-    if (!((fwd->flags | inv->flags) & NTTB200_FORCE_GENERIC) && fwd->logn >= 9 && fwd->logn <= 11 &&
+    if (!((fwd->flags | inv->flags) & NTTB200_FORCE_GENERIC) && fwd->logn >= 6 && fwd->logn <= 11 &&
         fwd->d_tw_r1 && inv->d_tw_r1 && batch % ((size_t) 2048 >> fwd->logn) == 0) {
         // N = 512..2048: warp-per-block CT, CT, then pointwise + inverse + scaling in one kernel
         NTTB200_CUDA(cudaMallocAsync(&tmp, sizeof(int32_t) * words * 2, st));

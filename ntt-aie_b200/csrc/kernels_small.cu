@@ -1,4 +1,4 @@
-// kernels_small.cu -- whole-transform register-radix kernel for N = 2^9 .. 2^11,
+// kernels_small.cu -- whole-transform register-radix kernels for N = 2^6 .. 2^11,
 // which includes the reference's own default N = 2048 (reference src/test.cpp:66,
 // src/aie2.py:14).
 //
@@ -388,7 +388,7 @@ static int small_set_attr() {
 }
 
 int small_prepare(nttb200_plan *p) {
-    if (p->logn < 9 || p->logn > 11) return NTTB200_ERR_UNSUPPORTED;
+    if (p->logn < 6 || p->logn > 11) return NTTB200_ERR_UNSUPPORTED;
     const uint32_t n = p->n;
     const int tpp = (int) (n >> 6);  // lanes per polynomial
     std::vector<uint2> host(n);
@@ -415,6 +415,9 @@ int small_prepare(nttb200_plan *p) {
         p->uni_gs.wp[i] = i < tpp ? host[i].y : 0;
     }
     switch (p->logn) {
+        case 6: return small_set_attr<6>();
+        case 7: return small_set_attr<7>();
+        case 8: return small_set_attr<8>();
         case 9: return small_set_attr<9>();
         case 10: return small_set_attr<10>();
         default: return small_set_attr<11>();
@@ -458,7 +461,7 @@ static void small_launch_t(int kind, int grid, cudaStream_t st, const CUtensorMa
 int launch_small(nttb200_plan *p, int kind, const int32_t *d_in, const int32_t *d_b, int32_t *d_out,
                  size_t batch, cudaStream_t st, size_t *done_polys) {
     *done_polys = 0;
-    if (p->logn < 9 || p->logn > 11 || !p->d_tw_r1) return NTTB200_ERR_UNSUPPORTED;
+    if (p->logn < 6 || p->logn > 11 || !p->d_tw_r1) return NTTB200_ERR_UNSUPPORTED;
     if (kind == 1 && p->logn != 11) return NTTB200_ERR_UNSUPPORTED;
     if (kind == 2 && !(p->q & 1u)) return NTTB200_ERR_UNSUPPORTED;
     const size_t per_block = (size_t) 2048 >> p->logn;
@@ -495,6 +498,9 @@ int launch_small(nttb200_plan *p, int kind, const int32_t *d_in, const int32_t *
     uint64_t ctas = (blocks + kS_Warps - 1) / kS_Warps;
     int grid = (int) (ctas < (uint64_t) p->sm_count ? ctas : (uint64_t) p->sm_count);
     switch (p->logn) {
+        case 6: small_launch_t<6>(kind, grid, st, lo, hi, blo, bhi, p->uni_gs, prm); break;
+        case 7: small_launch_t<7>(kind, grid, st, lo, hi, blo, bhi, p->uni_gs, prm); break;
+        case 8: small_launch_t<8>(kind, grid, st, lo, hi, blo, bhi, p->uni_gs, prm); break;
         case 9: small_launch_t<9>(kind, grid, st, lo, hi, blo, bhi, p->uni_gs, prm); break;
         case 10: small_launch_t<10>(kind, grid, st, lo, hi, blo, bhi, p->uni_gs, prm); break;
         default: small_launch_t<11>(kind, grid, st, lo, hi, blo, bhi, p->uni_gs, prm); break;

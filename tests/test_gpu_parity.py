@@ -340,7 +340,7 @@ def test_large_n_multi_pass_path(lib, oracle_mod, logn):
         assert np.array_equal(out, oracle_mod.ntt_gs(a, table, Q29)), (logn, batch, "in place")
 
 
-@pytest.mark.parametrize("logn", [9, 10, 11])
+@pytest.mark.parametrize("logn", [6, 7, 8, 9, 10, 11])
 def test_small_n_warp_kernel_ragged_batches(lib, oracle_mod, logn):
     """N = 512..2048 run one warp per 2048-coefficient block; batches that are not a
     multiple of the block (tail through the generic pass), in place, 12-bit and
@@ -449,7 +449,7 @@ def test_rns_batches(lib, oracle_mod):
             assert np.array_equal(d_a.cpu().numpy()[:, l], oracle_mod.ntt_gs(a[:, l], inv_t[l], q))
 
 
-@pytest.mark.parametrize("logn", [9, 10, 11])
+@pytest.mark.parametrize("logn", [6, 7, 8, 9, 10, 11])
 def test_small_n_ct_and_polymul_fast_paths(lib, oracle_mod, logn):
     """N = 512..2048: warp-per-block forward (CT) kernel and the product kernel
     (pointwise + inverse + N^-1 in one launch), whole and ragged batches, q = 3329-like
@@ -458,7 +458,7 @@ def test_small_n_ct_and_polymul_fast_paths(lib, oracle_mod, logn):
     rng = np.random.default_rng(14000 + logn)
     for q, g in ((Q29, 3), (12289, 11)):
         fwd, inv = lib.negacyclic_tables(n, q, g)
-        for batch in (8, 9, 64):
+        for batch in (32, 33, 64):
             a = rng.integers(0, q, (batch, n), dtype=np.int32)
             b = rng.integers(0, q, (batch, n), dtype=np.int32)
             a[0] = q - 1

@@ -11,7 +11,7 @@ cfg3  negacyclic polynomial multiply sweep N = 2^12 .. 2^16, batch = 2^26/N prod
       products/s and algorithmic GB/s (12 N bytes per product) vs the measured HBM peak.
 cfg4  batched NTT N = 2^16, 4096 polynomials (2^28 coefficients) on this GPU's shard:
       polys/s and algorithmic GB/s (8 N bytes per polynomial).
-ntt   forward GS NTT sweep N = 2^10 .. 2^16 at 2^26 coefficients (context for cfg3/4).
+ntt   forward GS NTT sweep N = 2^7 .. 2^16 at 2^26 coefficients (context for cfg3/4).
 
 One JSON line per measurement on stdout.  Device-timed with CUDA events on the
 launching stream, 3 warm-ups, inputs larger than L2.  Every timed configuration is
@@ -200,7 +200,7 @@ def main():
     if "1" in todo:
         cfg1(args.reps)
     if "ntt" in todo:
-        ntt_sweep(args.reps, range(10, 17))
+        ntt_sweep(args.reps, range(7, 17))  # the reference profiles logN 7..13
     if "3s" in todo:
         cfg3(args.reps, range(9, 12))      # below the BASELINE sweep: the reference's own N = 2048
     if "3" in todo:
