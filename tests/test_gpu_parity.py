@@ -278,6 +278,13 @@ def test_cpp_host_harness(lib):
         assert res.returncode == 0 and "PASS!" in res.stdout, res.stdout + res.stderr
 
 
+def _free_port():
+    import socket
+    with socket.socket() as sock:
+        sock.bind(("127.0.0.1", 0))
+        return sock.getsockname()[1]
+
+
 def test_fourstep_on_available_gpus(lib):
     """tools/fourstep_run.py under torchrun on min(2, #GPUs) ranks: the whole N=2^18
     vector bit-exact against the golden, for the reference table and an arbitrary one."""
@@ -292,7 +299,8 @@ def test_fourstep_on_available_gpus(lib):
         variants.append(["--fused", "--arbitrary-table"])   # transposes fused into peer stores
     for extra in variants:
         cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1",
-               f"--nproc-per-node={world}", "--master-addr", "127.0.0.1", "--master-port", "29533",
+               f"--nproc-per-node={world}", "--master-addr", "127.0.0.1", "--master-port",
+               str(_free_port()),
                os.path.join(root, "tools", "fourstep_run.py"), "--logn", "18", "--verify",
                "--steps", "1", "--warmup", "1"] + extra
         res = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
