@@ -26,6 +26,13 @@ sys.path.insert(0, ROOT)
 Q = 469762049
 
 
+def hbm_peak():
+    try:
+        return float(json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"])
+    except Exception:
+        return 6650.0
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--logn", type=int, default=26)
@@ -107,6 +114,29 @@ def main():
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         a2a_ms = float(t.item())
 
+    # the local phases alone (HBM roofline of the passes): step 1 on the shard, step 3 on scratch
+    def timed_fn(fn):
+        for _ in range(2):
+            fn()
+        sync()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(args.steps):
+            fn()
+        e1.record()
+        sync()
+        t = torch.tensor([e0.elapsed_time(e1) / args.steps], dtype=torch.float64, device="cuda")
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    eng = plan.engine
+    ms_local = timed_fn(lambda: eng.local_full(shard))
+    ms_cross = None
+    if world > 1:
+        logc = plan.logs - (world.bit_length() - 1)
+        ms_cross = timed_fn(lambda: eng.cross_stages(scratch, logc, plan.logs))
+
     ok = None
     if args.verify:
         shard.copy_(shard0)
@@ -136,6 +166,10 @@ def main():
             "all_to_all_ms": a2a_ms,
             "all_to_all_GBps_per_gpu_per_dir": (sent / (a2a_ms * 1e-3) / 1e9) if a2a_ms else None,
             "nvlink_peak_GBps_per_dir": 900.0, "nvlink_measured_peer_copy_GBps": 770.0,
+            "local_stages_ms": ms_local, "cross_stages_ms": ms_cross,
+            "local_stages_algorithmic_GBps_per_gpu": 8 * s / (ms_local * 1e-3) / 1e9,
+            "local_stages_frac_of_measured_hbm": 8 * s / (ms_local * 1e-3) / 1e9 / hbm_peak(),
+            "cross_stages_frac_of_measured_hbm": (8 * s / (ms_cross * 1e-3) / 1e9 / hbm_peak()) if ms_cross else None,
             "table_build_s": t_table, "bit_exact_vs_golden": ok,
         }
         if args.verify:
