@@ -16,6 +16,16 @@
 // Each pass costs one HBM read + one HBM write (8 bytes per coefficient).  This is
 // the GPU analogue of the reference's tile-local stages followed by cross-tile
 // stages (src/aie2.py:178-295, src/aie_core.cc:161-187).
+//
+// Also in this file (all built from the same team/tile machinery):
+//   poly_gs_kernel / poly_ct_kernel   N = 2^13..2^15 in ONE pass: the tiles of a polynomial
+//                                     on G teams of one CTA, cross-tile stages in a third
+//                                     register round through the tile buffers
+//   tile_ct_kernel / tile_ct_db_kernel  the forward (Cooley-Tukey) tile pass, output through
+//                                     a TMA store; MULT fuses a pointwise product
+//   tile_gs_kernel<DUAL>              pointwise product at load + N^-1 at the store
+//   template flag RNS                 tile position = residue channel with its own modulus
+//   column_kernel<.., SCATTER>        the multi-GPU exchange as NVLink peer stores
 #include <stdlib.h>
 
 #include <vector>
