@@ -138,6 +138,23 @@ __device__ __forceinline__ void ct_round(uint32_t (&v)[64], const TW tw, uint32_
     ct_stage_t<0, true>(v, tw, q, two_q, zero);
 }
 
+// CT stage K on registers that pair rows i and i + 2^K of one column, twiddles that do not
+// depend on the thread (table[(32 >> K) + block]) straight from the constant bank
+template <int K, bool REDUCE_X>
+__device__ __forceinline__ void ct_stage_uniform(uint32_t (&v)[64], const UniformTw &u, uint32_t q,
+                                                 uint32_t two_q, uint32_t zero) {
+    constexpr int kStride = 1 << K;
+#pragma unroll
+    for (int b = 0; b < (32 >> K); b++) {
+        const uint32_t w = u.w[(32 >> K) + b], wp = u.wp[(32 >> K) + b];
+#pragma unroll
+        for (int e = 0; e < kStride; e++) {
+            int i0 = b * 2 * kStride + e;
+            ct_bfly<REDUCE_X>(v[i0], v[i0 + kStride], w, wp, q, two_q, zero);
+        }
+    }
+}
+
 constexpr int kM_SmemBytesTw = kM_SmemBytes + kM_TwTile * 16;  // + one shared twiddle table
 
 struct TileParams {
@@ -684,7 +701,7 @@ __global__ void __launch_bounds__(kD_Threads, 1)
 tile_ct_db_kernel(const __grid_constant__ CUtensorMap map_lo, const __grid_constant__ CUtensorMap map_hi,
                   const __grid_constant__ CUtensorMap out_lo, const __grid_constant__ CUtensorMap out_hi,
                   const __grid_constant__ CUtensorMap mul_lo, const __grid_constant__ CUtensorMap mul_hi,
-                  const TileParams prm) {
+                  const __grid_constant__ UniformTw uni, const TileParams prm) {
     extern __shared__ uint8_t smem_raw[];
     const uint32_t data_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
     const uint32_t bar_base = data_base + kD_Teams * 2 * kF_PolyBytes;   // 2 mbarriers per team
@@ -747,7 +764,13 @@ tile_ct_db_kernel(const __grid_constant__ CUtensorMap map_lo, const __grid_const
         for (int i = 0; i < 64; i++) {
             v[i] = lds32(r2_col + i * 128 + (r2_chunk ^ ((i & 7) << 4)));
         }
-        ct_round<false>(v, TwShared{tws + 64 * 16}, q, two_q, zero);
+        // stages 11..6: twiddles table[1..63] from the constant bank
+        ct_stage_uniform<5, false>(v, uni, q, two_q, zero);
+        ct_stage_uniform<4, true>(v, uni, q, two_q, zero);
+        ct_stage_uniform<3, true>(v, uni, q, two_q, zero);
+        ct_stage_uniform<2, true>(v, uni, q, two_q, zero);
+        ct_stage_uniform<1, true>(v, uni, q, two_q, zero);
+        ct_stage_uniform<0, true>(v, uni, q, two_q, zero);
 #pragma unroll
         for (int i = 0; i < 64; i++) {
             asm volatile("st.shared.u32 [%0], %1;" ::"r"(r2_col + i * 128 + (r2_chunk ^ ((i & 7) << 4))),
@@ -1506,15 +1529,15 @@ int launch_multi_ct_mul(nttb200_plan *p, const int32_t *d_in, const int32_t *d_m
         tp.qinv = inv_mod_2_32(p->q);
     }
     static const bool use_db = getenv("NTTB200_CT_SINGLE_BUFFER") == nullptr;
-    if (tp.chunks == 1 && use_db) {
+    if (tp.chunks == 1 && use_db && p->d_tw_r1) {  // d_tw_r1 set <=> uni_gs holds table[1..63]
         uint64_t ctas = (tiles + kD_Teams - 1) / kD_Teams;
         int grid = (int) (ctas < (uint64_t) p->sm_count ? ctas : (uint64_t) p->sm_count);
         if (d_mul) {
             tile_ct_db_kernel<true><<<grid, kD_Threads, kD_SmemBytes, st>>>(in_lo, in_hi, out_lo, out_hi,
-                                                                           mul_lo, mul_hi, tp);
+                                                                           mul_lo, mul_hi, p->uni_gs, tp);
         } else {
             tile_ct_db_kernel<false><<<grid, kD_Threads, kD_SmemBytes, st>>>(in_lo, in_hi, out_lo, out_hi,
-                                                                            in_lo, in_hi, tp);
+                                                                            in_lo, in_hi, p->uni_gs, tp);
         }
     } else if (tp.chunks == 1) {
         if (d_mul) {
