@@ -58,6 +58,12 @@ typedef enum nttb200_status {
                                     /* AIE device leaves it (src/test.cpp:69-71,212-219); N>=16  */
 #define NTTB200_FORCE_GENERIC 2u    /* debugging: always take the generic stage-pass kernels     */
 
+#define NTTB200_REDUCE_INPUT 4u     /* nttb200_gs_batch / ct_batch accept ANY int32 words and reduce */
+                                    /* them mod q first, as the golden's `%` does on first touch     */
+                                    /* (src/test.cpp:46-50; e.g. a[i] = i with n > p); costs one     */
+                                    /* extra pass.  Without it device inputs must be in [0, q).      */
+                                    /* nttb200_gs_host always reduces (the pass hides behind PCIe).  */
+
 #define NTTB200_MAX_LOGN 27
 
 /* Opaque plan: owns the device copies of the twiddle table (+ Shoup companions
@@ -93,6 +99,28 @@ NTTB200_API int32_t nttb200_powmod(int32_t b, int64_t e, int32_t m);
 NTTB200_API int nttb200_plan_create(nttb200_plan **plan, int device, uint32_t logn, uint32_t q,
                                     const int32_t *table_host, uint32_t flags);
 NTTB200_API int nttb200_plan_destroy(nttb200_plan *plan);
+
+/* Same plan, but the table is GENERATED ON THE DEVICE -- the host ships nothing
+ * (the reference builds its table on the host and syncs it to the device,
+ * src/test.cpp:27-32,137-151; at N = 2^26 that is a 256 MiB upload per plan):
+ *     table[h + i] = gen(h * block_mult + i),   h = 1, 2, .., N/2,  i < h,  table[0] = 1
+ *     NTTB200_GEN_POWERS: gen(e) = base^e mod q
+ *     NTTB200_GEN_BITREV: gen(e) = base^bitrev(e) mod q, bit reversal over gen_logn bits
+ * With gen_logn = logn and block_mult = 1 these are make_roots (base = g^((q-1)/N)) and
+ * nttb200_make_bitrev_table.  gen_logn > logn with block_mult = G + r gives rank r's local
+ * table of a transform of length 2^gen_logn split over G = 2^(gen_logn-logn) devices
+ * (the derived table T_r of the four-step split), block_mult = 1 its cross-device table.
+ * Needs (N/2) * (block_mult + 1) <= 2^gen_logn and base < q. */
+#define NTTB200_GEN_POWERS 0u
+#define NTTB200_GEN_BITREV 1u
+NTTB200_API int nttb200_plan_create_generated(nttb200_plan **plan, int device, uint32_t logn,
+                                              uint32_t q, uint32_t kind, uint32_t base,
+                                              uint32_t gen_logn, uint32_t block_mult,
+                                              uint32_t flags);
+
+/* Copies the plan's table (N words, the w values; table[0] reported as 1) to the host:
+ * what the reference would have had in bo_root (src/test.cpp:119-120). */
+NTTB200_API int nttb200_plan_table(const nttb200_plan *plan, int32_t *table_host);
 
 /* ---- the hot path ---------------------------------------------------------- */
 
@@ -148,6 +176,11 @@ NTTB200_API int nttb200_gs_host(nttb200_plan *plan, const int32_t *h_in, int32_t
  * `.map<int32_t*>()` (src/test.cpp:115-134).  write_combined != 0 asks for
  * write-combined memory (fast for the device to read, slow for the CPU to read back:
  * use it for inputs only). */
+/* out[i] = in[i] mod q in [0, q) for ANY int32 words (device pointers): the reduction the
+ * golden applies with `%` when it first touches an input (src/test.cpp:46-50). */
+NTTB200_API int nttb200_reduce(nttb200_plan *plan, const int32_t *d_in, int32_t *d_out,
+                               size_t count, void *cuda_stream);
+
 NTTB200_API int nttb200_host_alloc(void **ptr, size_t bytes, int write_combined);
 NTTB200_API int nttb200_host_free(void *ptr);
 

@@ -18,6 +18,9 @@ from .api import (  # noqa: F401
     ORDER_AIE_DEVICE,
     ORDER_GOLDEN,
     FORCE_GENERIC,
+    REDUCE_INPUT,
+    GEN_POWERS,
+    GEN_BITREV,
     kernel_launches,
     lib_path,
     load_library,

@@ -15,6 +15,9 @@ _LIB_PATH = os.path.join(_HERE, "lib", "libnttb200.so")
 ORDER_GOLDEN = 0
 ORDER_AIE_DEVICE = 1
 FORCE_GENERIC = 2
+REDUCE_INPUT = 4
+GEN_POWERS = 0
+GEN_BITREV = 1
 
 _lib = None
 _i32p = ctypes.POINTER(ctypes.c_int32)
@@ -52,6 +55,10 @@ def load_library():
         "nttb200_plan_create": (ctypes.c_int, [ctypes.POINTER(vp), ctypes.c_int, u32, u32, _i32p,
                                                u32]),
         "nttb200_plan_destroy": (ctypes.c_int, [vp]),
+        "nttb200_plan_create_generated": (ctypes.c_int, [ctypes.POINTER(vp), ctypes.c_int, u32, u32, u32,
+                                                         u32, u32, u32, u32]),
+        "nttb200_plan_table": (ctypes.c_int, [vp, _i32p]),
+        "nttb200_reduce": (ctypes.c_int, [vp, vp, vp, sz, vp]),
         "nttb200_gs_batch": (ctypes.c_int, [vp, vp, vp, sz, ctypes.c_int, vp]),
         "nttb200_ct_batch": (ctypes.c_int, [vp, vp, vp, sz, ctypes.c_int, vp]),
         "nttb200_gs_stage_range": (ctypes.c_int, [vp, vp, vp, sz, ctypes.c_int, ctypes.c_int, vp]),
@@ -88,7 +95,8 @@ def load_library():
 
 EXPORTED_SYMBOLS = (
     "nttb200_make_roots", "nttb200_make_bitrev_table", "nttb200_powmod", "nttb200_plan_create",
-    "nttb200_plan_destroy", "nttb200_gs_batch", "nttb200_ct_batch", "nttb200_gs_stage_range",
+    "nttb200_plan_destroy", "nttb200_plan_create_generated", "nttb200_plan_table", "nttb200_reduce",
+    "nttb200_gs_batch", "nttb200_ct_batch", "nttb200_gs_stage_range",
     "nttb200_gs_host", "nttb200_gs_stage_range_scatter", "nttb200_host_alloc", "nttb200_host_free",
     "nttb200_pointwise", "nttb200_scale", "nttb200_polymul_negacyclic",
     "nttb200_rns_plan_create", "nttb200_rns_plan_destroy", "nttb200_rns_gs_batch",
@@ -202,6 +210,22 @@ class Plan:
         self._h = handle
         self.logn, self.n, self.q, self.device, self.flags = logn, 1 << logn, q, device, flags
 
+    @classmethod
+    def generated(cls, logn: int, q: int, kind: int, base: int, gen_logn: Optional[int] = None,
+                  block_mult: int = 1, device: int = 0, flags: int = 0) -> "Plan":
+        """Plan whose table is generated ON THE DEVICE (nothing is shipped):
+        table[h+i] = gen(h*block_mult + i), gen(e) = base^e (GEN_POWERS) or
+        base^bitrev(e) over gen_logn bits (GEN_BITREV).  See nttb200_plan_create_generated."""
+        self = cls.__new__(cls)
+        self._lib = load_library()
+        handle = ctypes.c_void_p()
+        _check(self._lib.nttb200_plan_create_generated(
+            ctypes.byref(handle), device, logn, q, kind, base,
+            logn if gen_logn is None else gen_logn, block_mult, flags), "plan_create_generated")
+        self._h = handle
+        self.logn, self.n, self.q, self.device, self.flags = logn, 1 << logn, q, device, flags
+        return self
+
     def close(self) -> None:
         if getattr(self, "_h", None):
             self._lib.nttb200_plan_destroy(self._h)
@@ -222,6 +246,17 @@ class Plan:
     @property
     def last_path(self) -> str:
         return self._lib.nttb200_plan_last_path(self._h).decode()
+
+    def table(self) -> np.ndarray:
+        """The plan's table as the reference host would hold it in bo_root."""
+        out = np.empty(self.n, dtype=np.int32)
+        _check(self._lib.nttb200_plan_table(self._h, out.ctypes.data_as(_i32p)), "plan_table")
+        return out
+
+    def reduce(self, d_in, d_out, count: int, stream=None) -> None:
+        """out = in mod q for arbitrary int32 words (the golden's `%` on first touch)."""
+        _check(self._lib.nttb200_reduce(self._h, _addr(d_in), _addr(d_out), count,
+                                        _stream(stream)), "reduce")
 
     def gs(self, d_in, d_out, batch: int, stage: int = -1, stream=None) -> None:
         """Golden network ``ntt(a, n, roots, p, stage)`` (src/test.cpp:34-60) on device."""
@@ -322,7 +357,9 @@ def ntt(a: np.ndarray, n: int, roots: np.ndarray, p: int, stage: int = -1, devic
         flags: int = 0) -> np.ndarray:
     """Drop-in for the golden call ``ntt(a, n, roots_rev, p, stage)`` (src/test.cpp:34):
     host arrays in, transformed copy out, computed on the GPU through
-    ``nttb200_gs_host``.  ``a`` may be 1-D (one polynomial) or 2-D (a batch)."""
+    ``nttb200_gs_host``.  ``a`` may be 1-D (one polynomial) or 2-D (a batch).  Like the
+    golden, inputs need not be reduced (``a[i] = i`` with n > p is fine): they are taken
+    mod p on first touch."""
     a = np.ascontiguousarray(a, dtype=np.int32)
     if a.shape[-1] != n or n & (n - 1) or n < 2:
         raise ValueError("last dimension must be n, a power of two >= 2")

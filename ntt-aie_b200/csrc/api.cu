@@ -11,6 +11,7 @@
 #include <string.h>
 
 #include <new>
+#include <stdexcept>
 #include <vector>
 
 #include "plan.h"
@@ -53,6 +54,20 @@ struct DeviceGuard {
         ok = cudaSetDevice(dev) == cudaSuccess;
     }
     ~DeviceGuard() {
+        if (prev >= 0) cudaSetDevice(prev);
+    }
+};
+
+// puts the caller's current device back when a constructor that switched devices returns
+struct DeviceRestore {
+    int prev = -1;
+    DeviceRestore() {
+        if (cudaGetDevice(&prev) != cudaSuccess) {
+            prev = -1;
+            cudaGetLastError();
+        }
+    }
+    ~DeviceRestore() {
         if (prev >= 0) cudaSetDevice(prev);
     }
 };
@@ -103,18 +118,20 @@ int32_t nttb200_powmod(int32_t b, int64_t e, int32_t m) {
 }
 
 /* ------------------------------------------------------------------ plan */
-int nttb200_plan_create(nttb200_plan **out, int device, uint32_t logn, uint32_t q,
-                        const int32_t *table_host, uint32_t flags) {
+}  // extern "C"
+
+// argument checks, device selection, plan object and the (w, w') table allocation shared by
+// the two constructors; on success the plan's device is current (guard)
+static int plan_begin(nttb200_plan **out, int device, uint32_t logn, uint32_t q, uint32_t flags,
+                      nttb200_plan **pp) {
     if (!out) return NTTB200_ERR_INVALID_ARG;
     *out = nullptr;
-    if (!table_host || logn < 1 || logn > NTTB200_MAX_LOGN) return NTTB200_ERR_INVALID_ARG;
-    if (flags & ~(NTTB200_ORDER_AIE_DEVICE | NTTB200_FORCE_GENERIC)) return NTTB200_ERR_INVALID_ARG;
+    if (logn < 1 || logn > NTTB200_MAX_LOGN) return NTTB200_ERR_INVALID_ARG;
+    if (flags & ~(NTTB200_ORDER_AIE_DEVICE | NTTB200_FORCE_GENERIC | NTTB200_REDUCE_INPUT)) {
+        return NTTB200_ERR_INVALID_ARG;
+    }
     if ((flags & NTTB200_ORDER_AIE_DEVICE) && logn < 4) return NTTB200_ERR_INVALID_ARG;
     if (q < 2 || q > (1u << 30)) return NTTB200_ERR_MODULUS;
-    const uint32_t n = 1u << logn;
-    for (uint32_t i = 1; i < n; i++) {  // table[0] is never read (src/test.cpp:45: h >= 1)
-        if (table_host[i] < 0 || (uint32_t) table_host[i] >= q) return NTTB200_ERR_TABLE;
-    }
     int count = 0;
     cudaError_t e = cudaGetDeviceCount(&count);
     if (e != cudaSuccess) return cuda_fail(e, "cudaGetDeviceCount");
@@ -122,14 +139,13 @@ int nttb200_plan_create(nttb200_plan **out, int device, uint32_t logn, uint32_t 
         snprintf(t_err, sizeof(t_err), "device %d not available (%d CUDA devices)", device, count);
         return NTTB200_ERR_NO_DEVICE;
     }
-    DeviceGuard guard(device);
-    if (!guard.ok) return cuda_fail(cudaGetLastError(), "cudaSetDevice");
-
+    e = cudaSetDevice(device);
+    if (e != cudaSuccess) return cuda_fail(e, "cudaSetDevice");
     nttb200_plan *p = new (std::nothrow) nttb200_plan();
     if (!p) return NTTB200_ERR_ALLOC;
     p->device = device;
     p->logn = logn;
-    p->n = n;
+    p->n = 1u << logn;
     p->q = q;
     p->flags = flags;
     p->mu = (uint64_t) ((((unsigned __int128) 1) << 62) / q);
@@ -140,67 +156,124 @@ int nttb200_plan_create(nttb200_plan **out, int device, uint32_t logn, uint32_t 
         p->n_inv = (uint32_t) powmod64((uint64_t) (q + 1) / 2, logn, q);
         p->n_inv_shoup = shoup_companion(p->n_inv, q);
     }
+    e = cudaMalloc(&p->d_tw, sizeof(uint2) * (size_t) p->n);
+    if (e != cudaSuccess) {
+        delete p;
+        return e == cudaErrorMemoryAllocation ? (cudaGetLastError(), NTTB200_ERR_ALLOC)
+                                              : cuda_fail(e, "cudaMalloc(table)");
+    }
+    *pp = p;
+    return NTTB200_OK;
+}
 
-    std::vector<uint2> tw;
-    try {
-        tw.resize(n);
+static void plan_abort(nttb200_plan *p) {
+    fused_release(p);
+    multi_release(p);
+    if (p->d_tw) cudaFree(p->d_tw);
+    delete p;
+}
+
+// kernel-family layouts derived from d_tw (all built on the device)
+static int plan_finish(nttb200_plan **out, nttb200_plan *p) {
+    int rc = generic_prepare();
+    try {  // the per-family staging vectors are small (<= 64 KiB) but no exception may cross the ABI
+        if (rc == NTTB200_OK && !(p->flags & NTTB200_FORCE_GENERIC)) {
+            rc = fused_prepare(p);
+            if (rc == NTTB200_ERR_UNSUPPORTED) rc = small_prepare(p);
+            if (rc == NTTB200_OK || rc == NTTB200_ERR_UNSUPPORTED) {
+                int rc2 = multi_prepare(p);
+                if (rc2 != NTTB200_ERR_UNSUPPORTED) rc = rc2;
+            }
+            if (rc == NTTB200_ERR_UNSUPPORTED) rc = NTTB200_OK;
+        }
     } catch (...) {
-        delete p;
-        return NTTB200_ERR_ALLOC;
+        rc = NTTB200_ERR_ALLOC;
     }
-    tw[0] = make_uint2(0, 0);
-    for (uint32_t i = 1; i < n; i++) {
-        uint32_t w = (uint32_t) table_host[i];
-        tw[i] = make_uint2(w, shoup_companion(w, q));
-    }
-    e = cudaMalloc(&p->d_tw, sizeof(uint2) * (size_t) n);
-    if (e != cudaSuccess) {
-        delete p;
-        return e == cudaErrorMemoryAllocation ? NTTB200_ERR_ALLOC : cuda_fail(e, "cudaMalloc(table)");
-    }
-    e = cudaMemcpy(p->d_tw, tw.data(), sizeof(uint2) * (size_t) n, cudaMemcpyHostToDevice);
-    if (e != cudaSuccess) {
-        cudaFree(p->d_tw);
-        delete p;
-        return cuda_fail(e, "cudaMemcpy(table)");
-    }
-    {
-        int rc = generic_prepare();
-        if (rc != NTTB200_OK) {
-            cudaFree(p->d_tw);
-            delete p;
-            return rc;
-        }
-    }
-    if (!(flags & NTTB200_FORCE_GENERIC)) {
-        int rc = fused_prepare(p);
-        if (rc == NTTB200_ERR_UNSUPPORTED) rc = small_prepare(p);
-        if (rc == NTTB200_OK || rc == NTTB200_ERR_UNSUPPORTED) {
-            int rc2 = multi_prepare(p);
-            if (rc2 != NTTB200_ERR_UNSUPPORTED) rc = rc2;
-        }
-        if (rc != NTTB200_OK && rc != NTTB200_ERR_UNSUPPORTED) {
-            fused_release(p);
-            multi_release(p);
-            cudaFree(p->d_tw);
-            delete p;
-            return rc;
-        }
+    if (rc != NTTB200_OK) {
+        plan_abort(p);
+        return rc;
     }
     *out = p;
     return NTTB200_OK;
 }
 
+extern "C" {
+
+int nttb200_plan_create(nttb200_plan **out, int device, uint32_t logn, uint32_t q,
+                        const int32_t *table_host, uint32_t flags) {
+    if (out) *out = nullptr;
+    if (!table_host || logn < 1 || logn > NTTB200_MAX_LOGN) return NTTB200_ERR_INVALID_ARG;
+    if (q >= 2 && q <= (1u << 30)) {
+        const uint32_t n = 1u << logn;
+        for (uint32_t i = 1; i < n; i++) {  // table[0] is never read (src/test.cpp:45: h >= 1)
+            if (table_host[i] < 0 || (uint32_t) table_host[i] >= q) return NTTB200_ERR_TABLE;
+        }
+    }
+    DeviceRestore restore;
+    nttb200_plan *p = nullptr;
+    int rc = plan_begin(out, device, logn, q, flags, &p);
+    if (rc != NTTB200_OK) return rc;
+    // ship the caller's int32 table; the Shoup companions are computed on the device
+    int32_t *d_table = nullptr;
+    cudaError_t e = cudaMalloc(&d_table, sizeof(int32_t) * (size_t) p->n);
+    if (e == cudaSuccess) {
+        e = cudaMemcpy(d_table, table_host, sizeof(int32_t) * (size_t) p->n, cudaMemcpyHostToDevice);
+    }
+    if (e == cudaSuccess) {
+        rc = build_shoup_table(p, d_table);
+        if (rc == NTTB200_OK) e = cudaDeviceSynchronize();
+    }
+    if (d_table) cudaFree(d_table);
+    if (e != cudaSuccess || rc != NTTB200_OK) {
+        plan_abort(p);
+        if (rc != NTTB200_OK) return rc;
+        return e == cudaErrorMemoryAllocation ? (cudaGetLastError(), NTTB200_ERR_ALLOC)
+                                              : cuda_fail(e, "table upload");
+    }
+    return plan_finish(out, p);
+}
+
+int nttb200_plan_create_generated(nttb200_plan **out, int device, uint32_t logn, uint32_t q,
+                                  uint32_t kind, uint32_t base, uint32_t gen_logn,
+                                  uint32_t block_mult, uint32_t flags) {
+    if (out) *out = nullptr;
+    if (kind > NTTB200_GEN_BITREV || gen_logn < logn || gen_logn > 31 || block_mult < 1) {
+        return NTTB200_ERR_INVALID_ARG;
+    }
+    // largest exponent: (N/2) * block_mult + N/2 - 1 must stay below 2^gen_logn
+    if (logn >= 1 && logn <= NTTB200_MAX_LOGN &&
+        ((uint64_t) 1 << (logn - 1)) * ((uint64_t) block_mult + 1) > ((uint64_t) 1 << gen_logn)) {
+        return NTTB200_ERR_INVALID_ARG;
+    }
+    if (q >= 2 && base >= q) return NTTB200_ERR_TABLE;
+    DeviceRestore restore;
+    nttb200_plan *p = nullptr;
+    int rc = plan_begin(out, device, logn, q, flags, &p);
+    if (rc != NTTB200_OK) return rc;
+    rc = build_generated_table(p, kind, base, gen_logn, block_mult);
+    if (rc != NTTB200_OK) {
+        plan_abort(p);
+        return rc;
+    }
+    return plan_finish(out, p);
+}
+
+int nttb200_plan_table(const nttb200_plan *p, int32_t *table_host) {
+    if (!p || !table_host) return NTTB200_ERR_INVALID_ARG;
+    DeviceGuard guard(p->device);
+    // the w halves of the (w, w') pairs, strided copy
+    NTTB200_CUDA(cudaMemcpy2D(table_host, sizeof(int32_t), p->d_tw, sizeof(uint2), sizeof(int32_t),
+                              p->n, cudaMemcpyDeviceToHost));
+    table_host[0] = 1;  // never read by the networks; the reference host sets roots[0] = 1
+    return NTTB200_OK;
+}
+
+static void host_release(nttb200_plan *p);
+
 int nttb200_plan_destroy(nttb200_plan *p) {
     if (!p) return NTTB200_OK;
     DeviceGuard guard(p->device);
-    if (p->host_ready) {
-        for (int k = 0; k < kHostStreams; k++) {
-            if (p->hstream[k]) cudaStreamSynchronize(p->hstream[k]);
-            if (p->d_stage[k]) cudaFree(p->d_stage[k]);
-            if (p->hstream[k]) cudaStreamDestroy(p->hstream[k]);
-        }
-    }
+    host_release(p);
     fused_release(p);
     multi_release(p);
     if (p->d_tw) cudaFree(p->d_tw);
@@ -210,7 +283,14 @@ int nttb200_plan_destroy(nttb200_plan *p) {
 
 /* -------------------------------------------------------------- hot path */
 static int run_gs(nttb200_plan *p, const int32_t *d_in, int32_t *d_out, size_t batch,
-                  int stage_limit, cudaStream_t st) {
+                  int stage_limit, cudaStream_t st, bool reduce_first = false) {
+    if (batch == 0) return NTTB200_OK;
+    if (reduce_first || (p->flags & NTTB200_REDUCE_INPUT)) {
+        // the golden's `%` on first touch (src/test.cpp:46-50): canonicalise, then in place
+        int rc = launch_reduce(p, d_in, d_out, batch * p->n, st);
+        if (rc != NTTB200_OK) return rc;
+        d_in = d_out;
+    }
     const bool full = full_depth(p, stage_limit);
     const bool permute = full && (p->flags & NTTB200_ORDER_AIE_DEVICE);
     if (full && !(p->flags & NTTB200_FORCE_GENERIC)) {
@@ -249,6 +329,12 @@ int nttb200_ct_batch(nttb200_plan *p, const int32_t *d_in, int32_t *d_out, size_
                      int stage_limit, void *stream) {
     if (!p || (batch && (!d_in || !d_out))) return NTTB200_ERR_INVALID_ARG;
     DeviceGuard guard(p->device);
+    if (batch == 0) return NTTB200_OK;
+    if (p->flags & NTTB200_REDUCE_INPUT) {
+        int rc = launch_reduce(p, d_in, d_out, batch * p->n, (cudaStream_t) stream);
+        if (rc != NTTB200_OK) return rc;
+        d_in = d_out;
+    }
     // CT stage idx (0 = stride N/2) acts on index bit logn-1-idx
     const bool full = full_depth(p, stage_limit);
     int sb = full ? 0 : (int) p->logn - 1 - stage_limit;
@@ -279,6 +365,7 @@ int nttb200_gs_stage_range(nttb200_plan *p, const int32_t *d_in, int32_t *d_out,
         return NTTB200_ERR_INVALID_ARG;
     }
     DeviceGuard guard(p->device);
+    if (batch == 0) return NTTB200_OK;
     if (stage_begin == stage_end) {
         if (d_in != d_out && batch) {
             NTTB200_CUDA(cudaMemcpyAsync(d_out, d_in, sizeof(int32_t) * batch * p->n,
@@ -317,6 +404,17 @@ int nttb200_gs_stage_range_scatter(nttb200_plan *p, int32_t *d_buf, int stage_be
                                    (cudaStream_t) stream);
 }
 
+static void host_release(nttb200_plan *p) {
+    for (int k = 0; k < kHostStreams; k++) {
+        if (p->hstream[k]) cudaStreamSynchronize(p->hstream[k]);
+        if (p->d_stage[k]) cudaFree(p->d_stage[k]);
+        if (p->hstream[k]) cudaStreamDestroy(p->hstream[k]);
+        p->d_stage[k] = nullptr;
+        p->hstream[k] = nullptr;
+    }
+    p->host_ready = false;
+}
+
 static int host_prepare(nttb200_plan *p) {
     if (p->host_ready) return NTTB200_OK;
     // staging buffers of 32 MiB each: deep enough to hide the PCIe latency,
@@ -329,8 +427,13 @@ static int host_prepare(nttb200_plan *p) {
     size_t polys = ((size_t) chunk_mb << 20) / (sizeof(int32_t) * p->n);
     if (polys < 1) polys = 1;
     for (int k = 0; k < kHostStreams; k++) {
-        NTTB200_CUDA(cudaStreamCreateWithFlags(&p->hstream[k], cudaStreamNonBlocking));
-        NTTB200_CUDA(cudaMalloc(&p->d_stage[k], sizeof(int32_t) * polys * p->n));
+        cudaError_t e = cudaStreamCreateWithFlags(&p->hstream[k], cudaStreamNonBlocking);
+        if (e == cudaSuccess) e = cudaMalloc(&p->d_stage[k], sizeof(int32_t) * polys * p->n);
+        if (e != cudaSuccess) {
+            host_release(p);  // nothing half-built is left behind
+            return e == cudaErrorMemoryAllocation ? (cudaGetLastError(), NTTB200_ERR_ALLOC)
+                                                  : cuda_fail(e, "host pipeline setup");
+        }
     }
     p->stage_polys = polys;
     p->host_ready = true;
@@ -347,25 +450,39 @@ int nttb200_gs_host(nttb200_plan *p, const int32_t *h_in, int32_t *h_out, size_t
     const size_t n = p->n;
     size_t done = 0;
     int k = 0;
-    while (done < batch) {
+    cudaError_t e = cudaSuccess;
+    while (done < batch && rc == NTTB200_OK && e == cudaSuccess) {
         size_t polys = batch - done < p->stage_polys ? batch - done : p->stage_polys;
         cudaStream_t st = p->hstream[k];
         int32_t *d = p->d_stage[k];
         // the stream is ordered: the previous D2H of this staging buffer has been
         // queued before this H2D, so the buffer is reused safely
-        NTTB200_CUDA(cudaMemcpyAsync(d, h_in + done * n, sizeof(int32_t) * polys * n,
-                                     cudaMemcpyHostToDevice, st));
-        rc = run_gs(p, d, d, polys, stage_limit, st);
-        if (rc != NTTB200_OK) return rc;
-        NTTB200_CUDA(cudaMemcpyAsync(h_out + done * n, d, sizeof(int32_t) * polys * n,
-                                     cudaMemcpyDeviceToHost, st));
+        e = cudaMemcpyAsync(d, h_in + done * n, sizeof(int32_t) * polys * n, cudaMemcpyHostToDevice, st);
+        // host inputs are whatever the caller's harness wrote (the reference fills a[i] = i,
+        // src/test.cpp:141): reduce them as the golden's `%` would; hidden behind the copies
+        if (e == cudaSuccess) rc = run_gs(p, d, d, polys, stage_limit, st, /*reduce_first=*/true);
+        if (e == cudaSuccess && rc == NTTB200_OK) {
+            e = cudaMemcpyAsync(h_out + done * n, d, sizeof(int32_t) * polys * n, cudaMemcpyDeviceToHost,
+                                st);
+        }
         done += polys;
         k = (k + 1) % kHostStreams;
     }
+    // always drain: no copy may still be writing h_out after this synchronous call returns
     for (int s = 0; s < kHostStreams; s++) {
-        NTTB200_CUDA(cudaStreamSynchronize(p->hstream[s]));
+        cudaError_t es = cudaStreamSynchronize(p->hstream[s]);
+        if (e == cudaSuccess) e = es;
     }
+    if (rc != NTTB200_OK) return rc;
+    if (e != cudaSuccess) return cuda_fail(e, "nttb200_gs_host");
     return NTTB200_OK;
+}
+
+int nttb200_reduce(nttb200_plan *p, const int32_t *d_in, int32_t *d_out, size_t count,
+                   void *stream) {
+    if (!p || (count && (!d_in || !d_out))) return NTTB200_ERR_INVALID_ARG;
+    DeviceGuard guard(p->device);
+    return launch_reduce(p, d_in, d_out, count, (cudaStream_t) stream);
 }
 
 int nttb200_host_alloc(void **ptr, size_t bytes, int write_combined) {
@@ -582,9 +699,11 @@ const char *nttb200_strerror(int status) {
 
 const char *nttb200_last_error(void) { return t_err; }
 uint64_t nttb200_kernel_launches(void) { return g_launches.load(std::memory_order_relaxed); }
-const char *nttb200_plan_last_path(const nttb200_plan *p) { return p ? p->last_path : "none"; }
+const char *nttb200_plan_last_path(const nttb200_plan *p) {
+    return p ? p->last_path.load(std::memory_order_relaxed) : "none";
+}
 uint32_t nttb200_plan_logn(const nttb200_plan *p) { return p ? p->logn : 0; }
 uint32_t nttb200_plan_modulus(const nttb200_plan *p) { return p ? p->q : 0; }
-const char *nttb200_version(void) { return "nttb200 0.1 (sm_100a)"; }
+const char *nttb200_version(void) { return "nttb200 0.2 (sm_100a)"; }
 
 }  // extern "C"

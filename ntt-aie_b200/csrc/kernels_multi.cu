@@ -1135,31 +1135,19 @@ int multi_set_attrs() {
 }
 
 int multi_prepare(nttb200_plan *p) {
-    if (p->logn < 12 || p->logn > 26) return NTTB200_ERR_UNSUPPORTED;
-    const uint32_t chunks = p->n >> 12;
-    std::vector<uint2> host(p->n);
-    NTTB200_CUDA(cudaMemcpy(host.data(), p->d_tw, sizeof(uint2) * p->n, cudaMemcpyDeviceToHost));
-    std::vector<uint4> t((size_t) chunks * kM_TwTile);
-    for (uint32_t c = 0; c < chunks; c++) {
-        for (int s = 0; s < 6; s++) {
-            const int blocks = 32 >> s;
-            const int slot0 = 32 - (blocks >= 2 ? blocks : 1);
-            for (int j = 0; j <= 64; j++) {
-                // j < 64: stage s of round 1, thread j; j == 64: stage 6+s of round 2
-                size_t base = j < 64
-                                  ? (size_t) (p->n >> (s + 1)) + (size_t) c * (2048 >> s) + (size_t) j * blocks
-                                  : (size_t) (p->n >> (s + 7)) + (size_t) c * blocks;
-                for (int b = 0; b < blocks; b += 2) {
-                    uint2 t0 = host[base + b];
-                    uint2 t1 = blocks >= 2 ? host[base + b + 1] : make_uint2(0, 0);
-                    t[(size_t) c * kM_TwTile + (size_t) (slot0 + b / 2) * kM_TwRow + j] =
-                        make_uint4(t0.x, t0.y, t1.x, t1.y);
-                }
-            }
-        }
+    if (p->logn < 12 || p->logn > NTTB200_MAX_LOGN) return NTTB200_ERR_UNSUPPORTED;
+    // [N/4096][32][65] uint4, gathered from d_tw by a kernel (tables.cu): at N = 2^26 this
+    // layout is 545 MB -- nothing of it is built on or shipped from the host
+    const size_t count = (size_t) (p->n >> 12) * kM_TwTile;
+    cudaError_t e = cudaMalloc(&p->d_tw_tile, sizeof(uint4) * count);
+    if (e != cudaSuccess) {
+        p->d_tw_tile = nullptr;
+        cudaGetLastError();
+        return e == cudaErrorMemoryAllocation ? NTTB200_ERR_ALLOC : cuda_fail(e, "cudaMalloc(tile table)");
     }
-    NTTB200_CUDA(cudaMalloc(&p->d_tw_tile, sizeof(uint4) * t.size()));
-    NTTB200_CUDA(cudaMemcpy(p->d_tw_tile, t.data(), sizeof(uint4) * t.size(), cudaMemcpyHostToDevice));
+    int rc = build_tile_table(p);
+    if (rc != NTTB200_OK) return rc;
+    NTTB200_CUDA(cudaDeviceSynchronize());
     return multi_set_attrs();
 }
 
@@ -1177,6 +1165,7 @@ static int launch_column(nttb200_plan *p, const int32_t *in, int32_t *out, size_
     cp.q = p->q;
     cp.zero = 0;
     cp.threads = ((uint64_t) batch << p->logn) >> (K + (VC == 4 ? 2 : VC == 2 ? 1 : 0));
+    if (cp.threads == 0) return NTTB200_OK;
     uint64_t blocks = (cp.threads + 255) / 256;
     uint64_t cap = (uint64_t) p->sm_count * 64;
     int grid = (int) (blocks < cap ? blocks : cap);
@@ -1430,7 +1419,8 @@ int launch_gs_range_scatter(nttb200_plan *p, int32_t *d_buf, int sb, int se, voi
     for (int k = 0; k < passes; k++) {
         int take = (rest + (passes - k) - 1) / (passes - k);
         const bool last = k == passes - 1;
-        if (last && take < log_g) return NTTB200_ERR_UNSUPPORTED;  // cannot happen for world <= 16
+        // the destination peer is chosen per element from idx >> slice_bits, independent of
+        // how many stages the last pass runs
         int rc = column_pass_t<false>(p, d_buf, d_buf, 1, s0, take, st, last ? &sc : nullptr);
         if (rc != NTTB200_OK) return rc;
         s0 += take;

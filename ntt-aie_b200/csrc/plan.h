@@ -39,7 +39,8 @@ struct nttb200_plan {
     uint4 *d_tw_tile = nullptr;      // [N/4096][32][65] tile-pass twiddles (logn 12..26)
     nttb200::UniformTw uni_gs{};     // round-2 uniform twiddles, GS network
     int sm_count = 148;
-    const char *last_path = "none";
+    // written by every launch, possibly from several host threads driving different streams
+    std::atomic<const char *> last_path{"none"};
 
     // nttb200_gs_host resources (lazily created, guarded by host_mu)
     std::mutex host_mu;
@@ -70,6 +71,13 @@ int cuda_fail(cudaError_t e, const char *what);
         cudaError_t e__ = (call);                                 \
         if (e__ != cudaSuccess) return ::nttb200::cuda_fail(e__, #call); \
     } while (0)
+
+// device-side table construction and input canonicalisation (tables.cu)
+int build_shoup_table(nttb200_plan *p, const int32_t *d_table);
+int build_generated_table(nttb200_plan *p, uint32_t kind, uint32_t base, uint32_t gen_logn,
+                          uint32_t block_mult);
+int build_tile_table(nttb200_plan *p);
+int launch_reduce(nttb200_plan *p, const int32_t *in, int32_t *out, size_t count, cudaStream_t st);
 
 // generic stage-pass kernels (kernels_generic.cu): stages [sb, se) of the GS
 // (ascending stride) or CT (descending stride) network; permute_out applies the

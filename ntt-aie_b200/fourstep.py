@@ -82,6 +82,20 @@ class CudaEngine:
         self.plan_local = api.Plan(logs, q, t_local, device=device)
         self.plan_cross = api.Plan(logs, q, t_cross, device=device)
 
+    @classmethod
+    def generated(cls, logn: int, logs: int, q: int, kind: int, base: int, world: int, rank: int,
+                  device: int) -> "CudaEngine":
+        """Both per-rank tables generated on the device from (kind, base): rank r's local
+        table is table[h*(G+r)+i], the cross table table[0..G) -- nothing is built on or
+        shipped from the host (nttb200_plan_create_generated)."""
+        from . import api
+        self = cls.__new__(cls)
+        self.plan_local = api.Plan.generated(logs, q, kind, base, gen_logn=logn,
+                                             block_mult=world + rank, device=device)
+        self.plan_cross = api.Plan.generated(logs, q, kind, base, gen_logn=logn, block_mult=1,
+                                             device=device)
+        return self
+
     def local_full(self, buf) -> None:
         self.plan_local.gs(buf, buf, 1)
 
@@ -116,8 +130,12 @@ class SymmetricBuffers:
 class FourStepNTT:
     """Golden GS network of length N = 2^logn over `world` ranks (power of two)."""
 
-    def __init__(self, logn: int, q: int, table: np.ndarray, rank: int, world: int,
-                 device: Optional[int] = None, engine=None, group=None, fused: bool = False):
+    def __init__(self, logn: int, q: int, table: Optional[np.ndarray], rank: int, world: int,
+                 device: Optional[int] = None, engine=None, group=None, fused: bool = False,
+                 generated: Optional[tuple] = None):
+        """`table`: the caller's length-N table (any residues), or None together with
+        `generated=(kind, base)` to have every rank generate its own tables on its GPU
+        (GEN_POWERS with base = g^((q-1)/N) is the reference's make_roots table)."""
         if world & (world - 1) or world < 1:
             raise ValueError("world size must be a power of two")
         self.logn, self.q, self.rank, self.world, self.group = logn, q, rank, world, group
@@ -126,20 +144,28 @@ class FourStepNTT:
         self.logs = logn - (world.bit_length() - 1)
         if self.shard < world:
             raise ValueError("shard must hold at least one element per peer")
-        table = np.ascontiguousarray(table, dtype=np.int32)
-        if table.shape[0] != self.n:
-            raise ValueError("table must hold N words")
-        self.t_local = local_table(table, world, rank)
-        self.t_cross = cross_table(table, world, self.shard)
-        self.engine = engine if engine is not None else CudaEngine(
-            self.logs, q, self.t_local, self.t_cross, 0 if device is None else device)
+        dev = 0 if device is None else device
+        if generated is not None:
+            if engine is not None or table is not None:
+                raise ValueError("generated tables need the CUDA engine and no host table")
+            kind, base = generated
+            self.t_local = self.t_cross = None
+            self.engine = CudaEngine.generated(logn, self.logs, q, kind, base, world, rank, dev)
+        else:
+            table = np.ascontiguousarray(table, dtype=np.int32)
+            if table.shape[0] != self.n:
+                raise ValueError("table must hold N words")
+            self.t_local = local_table(table, world, rank)
+            self.t_cross = cross_table(table, world, self.shard)
+            self.engine = engine if engine is not None else CudaEngine(
+                self.logs, q, self.t_local, self.t_cross, dev)
         self.symm = None
         if fused and world > 1:
             if engine is not None:
                 raise ValueError("the fused exchange needs the CUDA engine")
             if self.logs < 13:
                 raise ValueError("fused exchange needs shards of at least 2^13 coefficients")
-            self.symm = SymmetricBuffers(self.shard, 0 if device is None else device, group)
+            self.symm = SymmetricBuffers(self.shard, dev, group)
 
     def close(self) -> None:
         if hasattr(self.engine, "close"):
@@ -166,9 +192,12 @@ class FourStepNTT:
 
     def _forward_fused(self, shard, natural_order: bool):
         """Steps 1-4 with both transposes fused into the passes' stores.  Returns the
-        symmetric buffer that holds the result (valid until the next call)."""
+        symmetric buffer that holds the result.  The result must be consumed on every rank
+        before any rank calls forward() again: the entry barrier below keeps a faster peer
+        from scattering its next step-1 results into a buffer this rank still reads."""
         eng, sy = self.engine, self.symm
         logc = self.logs - (self.world.bit_length() - 1)
+        sy.barrier()                      # every rank is done with the previous call's buffers
         # steps 1+2: local stages; the last pass scatters into every rank's scratch
         eng.plan_local.gs_stage_range_scatter(shard, 0, self.logs, sy.scratch_ptrs, self.rank)
         sy.barrier()                      # all slices have landed everywhere

@@ -294,9 +294,10 @@ def test_fourstep_on_available_gpus(lib):
     import sys
     root = os.path.dirname(os.path.dirname(os.path.dirname(lib.lib_path())))
     world = min(2, torch.cuda.device_count())
-    variants = [[], ["--arbitrary-table"]]
+    variants = [[], ["--arbitrary-table"], ["--generated"]]
     if world > 1:
         variants.append(["--fused", "--arbitrary-table"])   # transposes fused into peer stores
+        variants.append(["--fused", "--generated"])
     for extra in variants:
         cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1",
                f"--nproc-per-node={world}", "--master-addr", "127.0.0.1", "--master-port",
@@ -307,6 +308,7 @@ def test_fourstep_on_available_gpus(lib):
         assert res.returncode == 0, res.stdout + res.stderr
         line = json.loads([l for l in res.stdout.splitlines() if l.startswith("{")][-1])
         assert line["bit_exact_vs_golden"] is True and line["n_gpus"] == world
+        assert line["bit_exact_transposed_order"] is True
 
 
 @pytest.mark.parametrize("logn", [6, 13, 17, 20])
@@ -510,3 +512,208 @@ def test_segmented_table_path(lib, oracle_mod):
     got = d_o.cpu().numpy()
     for l, q in enumerate(qs):
         assert np.array_equal(got[:, l], oracle_mod.ntt_gs(a[:, l], tabs[l], q)), l
+
+
+# ------------------------------------------------------------------ round 2 additions
+def _golden_dir():
+    import os
+    return os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+@pytest.mark.parametrize("logn,world", [(16, 2), (16, 4), (16, 8), (18, 4), (17, 8)])
+def test_scatter_kernels_with_self_peers(lib, oracle_mod, logn, world):
+    """nttb200_gs_stage_range_scatter on ONE GPU: every "peer" buffer lives on this device,
+    the ranks run one after the other.  Exercises column_kernel<.., SCATTER=true>, its peer
+    index math, the tile pass + scatter (stage_begin == 0) and the cross-device pass +
+    return scatter (stage_begin == log2(S/G)); the reassembled vector must equal the golden
+    transform of the whole input, the intermediate the transposed local results."""
+    from test_multigpu_cpu import gs_stage_range_numpy
+    import ntt_aie_b200.fourstep as fs
+    n, s = 1 << logn, (1 << logn) // world
+    logs, c = logn - (world.bit_length() - 1), s // world
+    rng = np.random.default_rng(16000 + logn + world)
+    table = rng.integers(0, Q29, n, dtype=np.int32)
+    a = rng.integers(0, Q29, n, dtype=np.int32)
+    want = oracle_mod.ntt_gs(a, table, Q29)
+    recv = [torch.zeros(s, dtype=torch.int32, device="cuda") for _ in range(world)]
+    final = [torch.zeros(s, dtype=torch.int32, device="cuda") for _ in range(world)]
+    recv_ptrs, final_ptrs = [t.data_ptr() for t in recv], [t.data_ptr() for t in final]
+    local_results = []
+    for r in range(world):                       # steps 1+2 of every rank
+        t_local = fs.local_table(table, world, r)
+        shard = dev(a[r * s:(r + 1) * s])
+        with lib.Plan(logs, Q29, t_local) as plan:
+            plan.gs_stage_range_scatter(shard, 0, logs, recv_ptrs, r)
+            torch.cuda.synchronize()
+            assert "scatter" in plan.last_path
+        local_results.append(oracle_mod.ntt_gs(a[r * s:(r + 1) * s], t_local, Q29))
+    for k in range(world):                       # rank k holds slice k of every shard
+        exp = np.concatenate([local_results[r][k * c:(k + 1) * c] for r in range(world)])
+        assert np.array_equal(recv[k].cpu().numpy(), exp), ("transpose", k)
+    t_cross = fs.cross_table(table, world, s)
+    logc = logs - (world.bit_length() - 1)
+    for k in range(world):                       # steps 3+4
+        exp3 = gs_stage_range_numpy(recv[k].cpu().numpy(), t_cross, Q29, logc, logs)
+        with lib.Plan(logs, Q29, t_cross) as plan:
+            plan.gs_stage_range_scatter(recv[k], logc, logs, final_ptrs, k)
+            torch.cuda.synchronize()
+        # the pass ran in place on everything but its scattered last stage group; compare
+        # through the reassembled result below and the stage-range restatement here
+        for r in range(world):
+            assert np.array_equal(final[r].cpu().numpy()[k * c:(k + 1) * c], exp3[r * c:(r + 1) * c])
+    got = np.concatenate([t.cpu().numpy() for t in final])
+    assert np.array_equal(got, want)
+
+
+@pytest.mark.parametrize("logn", [22, 24, 26, 27])
+def test_large_transforms_against_reference_digests(lib, logn):
+    """One N = 2^22 / 2^24 / 2^26 (BASELINE configs[4] size) / 2^27 transform against the
+    digest of the reference's own golden output (tests/golden/make_golden_large.py); table
+    shipped from the host AND generated on the device."""
+    import os
+    from tools.digest import as_unsigned, digest_numpy, digest_torch
+    g = np.load(os.path.join(_golden_dir(), "large_digests.npz"))
+    n, q = 1 << logn, int(g["q"])
+    a = np.random.default_rng(int(g["seed"]) + logn).integers(0, q, n, dtype=np.int32)
+    assert digest_numpy(a) == tuple(int(v) for v in g[f"in_digest_{logn}"])
+    d_in = dev(a)
+    d_out = torch.empty_like(d_in)
+    want = tuple(int(v) for v in g[f"digest_{logn}"])
+    w = lib.powmod(int(g["g"]), (q - 1) // n, q)
+    plans = [lambda: lib.Plan.generated(logn, q, lib.GEN_POWERS, w)]
+    if logn <= 26:
+        plans.append(lambda: lib.Plan(logn, q, lib.make_roots(n, q, int(g["g"]))))
+    for make in plans:
+        d_out.zero_()
+        with make() as plan:
+            plan.gs(d_in, d_out, 1)
+            torch.cuda.synchronize()
+            assert "tile" in plan.last_path, plan.last_path
+        assert as_unsigned(digest_torch(d_out)) == want, logn
+        assert np.array_equal(d_out[:16].cpu().numpy(), g[f"head_{logn}"])
+        assert np.array_equal(d_out[-16:].cpu().numpy(), g[f"tail_{logn}"])
+    # in place
+    with plans[0]() as plan:
+        plan.gs(d_in, d_in, 1)
+        torch.cuda.synchronize()
+    assert as_unsigned(digest_torch(d_in)) == want
+
+
+@pytest.mark.parametrize("logn", [1, 4, 11, 12, 13, 16, 20])
+def test_generated_tables_match_host_tables(lib, logn):
+    """nttb200_plan_create_generated: tables built on the device equal make_roots /
+    make_bitrev_table / the four-step derived tables built on the host, word for word,
+    and transform identically."""
+    import ntt_aie_b200.fourstep as fs
+    n = 1 << logn
+    for q, g in ((Q29, 3), (3329, 3), (Q30, 7)):
+        w = lib.powmod(g, (q - 1) // n, q)
+        with lib.Plan.generated(logn, q, lib.GEN_POWERS, w) as plan:
+            assert np.array_equal(plan.table(), lib.make_roots(n, q, g)), (logn, q)
+        base = 12345 % q
+        with lib.Plan.generated(logn, q, lib.GEN_BITREV, base) as plan:
+            assert np.array_equal(plan.table(), lib.make_bitrev_table(n, q, base)), (logn, q)
+    # four-step derived tables of a global transform of length 2^(logn+3) on 8 ranks
+    world, glog = 8, logn + 3
+    if glog <= 22:
+        w = lib.powmod(3, (Q29 - 1) >> glog, Q29)
+        table = lib.make_roots(1 << glog, Q29, 3)
+        bt = lib.make_bitrev_table(1 << glog, Q29, 777)
+        for r in (0, 5, 7):
+            with lib.Plan.generated(logn, Q29, lib.GEN_POWERS, w, gen_logn=glog, block_mult=world + r) as p:
+                assert np.array_equal(p.table()[1:], fs.local_table(table, world, r)[1:])
+            with lib.Plan.generated(logn, Q29, lib.GEN_BITREV, 777, gen_logn=glog, block_mult=world + r) as p:
+                assert np.array_equal(p.table()[1:], fs.local_table(bt, world, r)[1:])
+        if n >= world:
+            with lib.Plan.generated(logn, Q29, lib.GEN_POWERS, w, gen_logn=glog) as p:
+                assert np.array_equal(p.table()[1:world], table[1:world])
+    a = np.random.default_rng(17000 + logn).integers(0, Q29, (3, n), dtype=np.int32)
+    w = lib.powmod(3, (Q29 - 1) // n, Q29)
+    d_in, d_out = dev(a), torch.empty(3, n, dtype=torch.int32, device="cuda")
+    with lib.Plan.generated(logn, Q29, lib.GEN_POWERS, w) as plan:
+        plan.gs(d_in, d_out, 3)
+    assert np.array_equal(d_out.cpu().numpy(), oracle_ntt(a, lib.make_roots(n, Q29, 3), Q29))
+
+
+def oracle_ntt(a, roots, p):
+    import oracle
+    return oracle.ntt_gs(a, roots, p)
+
+
+def test_unreduced_inputs_like_the_reference_harness(lib, oracle_mod):
+    """The reference harness feeds a[i] = i (src/test.cpp:141); at its larger sizes
+    (N = 4096, 8192 with p = 3329) that is not reduced and the golden takes it mod p on
+    first touch.  nttb200_gs_host / ntt() reduce always; device entry points with the
+    REDUCE_INPUT plan flag; nttb200_reduce by itself."""
+    import os
+    g = np.load(os.path.join(_golden_dir(), "unreduced_inputs.npz"))
+    for n in (4096, 8192):
+        a = np.arange(n, dtype=np.int32)
+        roots = g[f"roots_{n}"]
+        assert np.array_equal(lib.ntt(a, n, roots, 3329), g[f"out_{n}"]), n
+        for flags in (lib.REDUCE_INPUT, lib.REDUCE_INPUT | lib.FORCE_GENERIC):
+            out, _ = run_gs(lib, a, roots, 3329, flags=flags)
+            assert np.array_equal(out, g[f"out_{n}"]), (n, flags)
+            out, _ = run_gs(lib, a, roots, 3329, flags=flags, inplace=True)
+            assert np.array_equal(out, g[f"out_{n}"]), (n, flags, "in place")
+    assert np.array_equal(lib.ntt(g["a_q29"], 4096, g["roots_q29"], Q29), g["out_q29"])
+    out, _ = run_gs(lib, g["a_q29"], g["roots_q29"], Q29, flags=lib.REDUCE_INPUT)
+    assert np.array_equal(out, g["out_q29"])
+    # nttb200_reduce: any int32, incl. negative (mapped to the mathematical residue), ragged
+    rng = np.random.default_rng(18000)
+    for q in (3329, Q29, 1 << 30, 2):
+        for count in (1, 5, 4096 + 3):
+            x = rng.integers(-(1 << 31), (1 << 31) - 1, count, dtype=np.int64).astype(np.int32)
+            with lib.Plan(4, q, np.zeros(16, np.int32)) as plan:
+                d = dev(x)
+                o = torch.empty_like(d)
+                plan.reduce(d, o, count)
+                assert np.array_equal(o.cpu().numpy(), (x.astype(np.int64) % q).astype(np.int32))
+                plan.reduce(d[1:], o[1:], count - 1)      # unaligned views
+                assert np.array_equal(o.cpu().numpy()[1:], (x[1:].astype(np.int64) % q).astype(np.int32))
+    # forward network with the flag
+    n = 4096
+    fwd, _ = lib.negacyclic_tables(n, Q29, 3)
+    a = g["a_q29"]
+    d_in, d_out = dev(a), torch.empty(n, dtype=torch.int32, device="cuda")
+    with lib.Plan(12, Q29, fwd, flags=lib.REDUCE_INPUT) as plan:
+        plan.ct(d_in, d_out, 1)
+    assert np.array_equal(d_out.cpu().numpy(), oracle_mod.ntt_ct((a.astype(np.int64) % Q29).astype(np.int32), fwd, Q29))
+
+
+def test_concurrent_launches_on_one_plan(lib, oracle_mod):
+    """one plan, several host threads, each on its own stream."""
+    import threading
+    n, p, batch = 4096, Q29, 64
+    roots = lib.make_roots(n, p, 3)
+    rng = np.random.default_rng(19000)
+    a = rng.integers(0, p, (4, batch, n), dtype=np.int32)
+    want = [oracle_mod.ntt_gs(a[k], roots, p) for k in range(4)]
+    outs = [None] * 4
+    with lib.Plan(12, p, roots) as plan:
+        def work(k):
+            st = torch.cuda.Stream()
+            d_in = dev(a[k])
+            d_out = torch.empty_like(d_in)
+            for _ in range(20):
+                plan.gs(d_in, d_out, batch, -1, st)
+                _ = plan.last_path
+            st.synchronize()
+            outs[k] = d_out.cpu().numpy()
+        threads = [threading.Thread(target=work, args=(k,)) for k in range(4)]
+        for t in threads:
+            t.start()
+        for t in threads:
+            t.join()
+    for k in range(4):
+        assert np.array_equal(outs[k], want[k]), k
+
+
+def test_stage_range_empty_batch_and_scatter_limits(lib):
+    n = 1 << 14
+    table = np.random.default_rng(3).integers(0, Q29, n, dtype=np.int32)
+    with lib.Plan(14, Q29, table) as plan:
+        plan.gs_stage_range(0, 0, 0, 2, 14)          # batch 0 with a column-pass range: OK, no launch
+        plan.gs_stage_range(0, 0, 0, 0, 14)
+        plan.gs(0, 0, 0)
+        plan.ct(0, 0, 0)

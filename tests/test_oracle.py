@@ -149,3 +149,50 @@ def test_device_barrett_agrees_with_golden_mod(oracle_mod):
             assert oracle_mod.barrett_2k(a, b, p, w, u) == a * b % p
             assert oracle_mod.modadd(a, b, p) == (a + b) % p
             assert oracle_mod.modsub(a, b, p) == (a - b) % p
+
+
+def test_position_weighted_digest_numpy_equals_torch():
+    """tools/digest.py: the numpy form (fixtures) and the torch form (GPU tests, bench.py)
+    agree, and the digest is additive over shards with their global offsets."""
+    import torch
+    from tools.digest import as_unsigned, digest_numpy, digest_torch
+    rng = np.random.default_rng(5)
+    x = rng.integers(0, 469762049, 100003, dtype=np.int32)
+    want = digest_numpy(x)
+    assert as_unsigned(digest_torch(torch.from_numpy(x))) == want
+    parts = torch.zeros(2, dtype=torch.int64)
+    for lo, hi in ((0, 17), (17, 50000), (50000, 100003)):
+        parts += digest_torch(torch.from_numpy(x[lo:hi]), offset=lo)
+    assert as_unsigned(parts) == want
+    y = x.copy()
+    y[[3, 99999]] = y[[99999, 3]]            # a swap changes it
+    assert digest_numpy(y) != want
+
+
+def test_large_digest_fixture_is_consistent():
+    """tests/golden/large_digests.npz was written from the reference's own golden output;
+    the N = 2^22 entry is cheap enough to recompute here with the restatement."""
+    import os
+    import oracle
+    from conftest import GOLDEN, Q29
+    from tools.digest import digest_numpy
+    g = np.load(os.path.join(GOLDEN, "large_digests.npz"))
+    logn = 22
+    a = np.random.default_rng(int(g["seed"]) + logn).integers(0, Q29, 1 << logn, dtype=np.int32)
+    out = oracle.ntt_gs(a, oracle.make_roots(1 << logn, Q29, 3), Q29)
+    assert digest_numpy(out) == tuple(int(v) for v in g[f"digest_{logn}"])
+    assert np.array_equal(out[:16], g[f"head_{logn}"]) and np.array_equal(out[-16:], g[f"tail_{logn}"])
+
+
+def test_unreduced_fixture_matches_restatement():
+    """a[i] = i with n > p (the reference harness input at its larger sizes): the golden's
+    `%` on first touch == reduce, then transform."""
+    import os
+    import oracle
+    from conftest import GOLDEN
+    g = np.load(os.path.join(GOLDEN, "unreduced_inputs.npz"))
+    for n in (4096, 8192):
+        a = np.arange(n, dtype=np.int32) % 3329
+        assert np.array_equal(oracle.ntt_gs(a, g[f"roots_{n}"], 3329), g[f"out_{n}"])
+    a = (g["a_q29"].astype(np.int64) % 469762049).astype(np.int32)
+    assert np.array_equal(oracle.ntt_gs(a, g["roots_q29"], 469762049), g["out_q29"])
