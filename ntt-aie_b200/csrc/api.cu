@@ -176,6 +176,7 @@ static void plan_abort(nttb200_plan *p) {
 // kernel-family layouts derived from d_tw (all built on the device)
 static int plan_finish(nttb200_plan **out, nttb200_plan *p) {
     int rc = generic_prepare();
+    if (rc == NTTB200_OK) rc = polymul_prepare();
     try {  // the per-family staging vectors are small (<= 64 KiB) but no exception may cross the ABI
         if (rc == NTTB200_OK && !(p->flags & NTTB200_FORCE_GENERIC)) {
             rc = fused_prepare(p);
@@ -533,6 +534,14 @@ int nttb200_polymul_negacyclic(nttb200_plan *fwd, nttb200_plan *inv, const int32
     DeviceGuard guard(fwd->device);
     cudaStream_t st = (cudaStream_t) stream;
     const size_t words = batch * fwd->n;
+    if (fwd->logn == 12 && !((fwd->flags | inv->flags) & NTTB200_FORCE_GENERIC)) {
+        // N = 4096: one kernel per product, operands and result cross HBM once (12 N bytes)
+        static const bool one_kernel = getenv("NTTB200_POLYMUL_3KERNEL") == nullptr;
+        if (one_kernel) {
+            int rc = launch_polymul4096(fwd, inv, d_a, d_b, d_c, batch, st);
+            if (rc != NTTB200_ERR_UNSUPPORTED) return rc;
+        }
+    }
     // scratch for NTT(b) (and NTT(a) when the output aliases b)
     int32_t *tmp = nullptr;
     const bool fast = !((fwd->flags | inv->flags) & NTTB200_FORCE_GENERIC) && fwd->d_tw_tile &&

@@ -111,4 +111,158 @@ __device__ __forceinline__ void tma_store_commit_and_wait_read() {
 }
 
 
+
+// ------------------------------------------------------------------ Tensor Memory
+// TMEM (256 KiB per SM: 128 lanes x 512 columns x 32 bit) as per-thread storage.  A warp
+// reaches the 32 lanes of its quadrant (warp id mod 4); with the 32x32b shape lane l of
+// the warp reads/writes `x N` consecutive columns of TMEM lane 32*(warp%4) + l.  The
+// NTT kernels keep each thread's PRIVATE twiddle pairs there (128 words per table: the
+// 32 uint4 slots of gs_stage_t / ct_stage_t), which frees 32 KiB of shared memory per
+// table and takes the twiddle reads off the shared-memory crossbar (measured on B200,
+// profiles/microbench/tmem.cu: 326 B/clk/SM for x16 loads against 128 B/clk/SM for
+// LDS.128), and park a transformed operand there while the second one is transformed
+// (polymul).  No tensor-core instruction is involved.  SASS: LDTM / STTM.
+__device__ __forceinline__ void tmem_alloc_512(uint32_t smem_slot) {  // one full warp
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(smem_slot)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc_512(uint32_t base) {    // the same warp
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(base) : "memory");
+}
+__device__ __forceinline__ void tmem_fence_before_sync() {
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_fence_after_sync() {
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+        "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+          "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]),
+          "=r"(r[15])
+        : "r"(taddr));
+}
+// The loaded registers pass THROUGH the wait ("+r"), so every use is ordered behind it.
+__device__ __forceinline__ void tmem_wait_ld16(uint32_t (&r)[16]) {
+    asm volatile("tcgen05.wait::ld.sync.aligned;"
+                 : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]),
+                   "+r"(r[7]), "+r"(r[8]), "+r"(r[9]), "+r"(r[10]), "+r"(r[11]), "+r"(r[12]),
+                   "+r"(r[13]), "+r"(r[14]), "+r"(r[15])
+                 :
+                 : "memory");
+}
+__device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t *r) {
+    asm volatile(
+        "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], "
+        "{%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16};" ::"r"(taddr),
+        "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]),
+        "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15])
+        : "memory");
+}
+__device__ __forceinline__ void tmem_wait_st() {
+    asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+}
+
+// NB consecutive blocks B0.. of stage S (pairs i, i + 2^S) with the (w, w') pairs of those
+// blocks in t[0..2*NB): the unit of work between two TMEM loads.
+template <int S, int B0, int NB, bool REDUCE>
+__device__ __forceinline__ void gs_blocks(uint32_t (&v)[64], const uint32_t *t, uint32_t q,
+                                          uint32_t two_q, uint32_t zero) {
+    constexpr int kStride = 1 << S;
+#pragma unroll
+    for (int k = 0; k < NB; k++) {
+#pragma unroll
+        for (int e = 0; e < kStride; e++) {
+            const int i0 = (B0 + k) * 2 * kStride + e;
+            gs_bfly<REDUCE>(v[i0], v[i0 + kStride], t[2 * k], t[2 * k + 1], q, two_q, zero);
+        }
+    }
+}
+template <int S, int B0, int NB, bool REDUCE_X>
+__device__ __forceinline__ void ct_blocks(uint32_t (&v)[64], const uint32_t *t, uint32_t q,
+                                          uint32_t two_q, uint32_t zero) {
+    constexpr int kStride = 1 << S;
+#pragma unroll
+    for (int k = 0; k < NB; k++) {
+#pragma unroll
+        for (int e = 0; e < kStride; e++) {
+            const int i0 = (B0 + k) * 2 * kStride + e;
+            ct_bfly<REDUCE_X>(v[i0], v[i0 + kStride], t[2 * k], t[2 * k + 1], q, two_q, zero);
+        }
+    }
+}
+
+// GS stages 0..5 on the thread's 64 registers, private twiddles from the thread's
+// 128-word TMEM table at `taddr` (slot layout of fused_prepare / tile_table_kernel:
+// slots 0-15 stage 0, 16-23 stage 1, 24-27 stage 2, 28-29 stage 3, 30 stage 4, 31 stage 5;
+// one x16 load = 4 slots = 8 pairs).  The next group's load is in flight while the current
+// group's butterflies run.
+template <bool REDUCE0>
+__device__ __forceinline__ void gs_round_tmem(uint32_t (&v)[64], uint32_t taddr, uint32_t q,
+                                              uint32_t two_q, uint32_t zero) {
+    uint32_t ta[16], tb[16];
+    tmem_ld16(taddr, ta);
+    tmem_wait_ld16(ta);
+    tmem_ld16(taddr + 16, tb);
+    gs_blocks<0, 0, 8, REDUCE0>(v, ta, q, two_q, zero);
+    tmem_wait_ld16(tb);
+    tmem_ld16(taddr + 32, ta);
+    gs_blocks<0, 8, 8, REDUCE0>(v, tb, q, two_q, zero);
+    tmem_wait_ld16(ta);
+    tmem_ld16(taddr + 48, tb);
+    gs_blocks<0, 16, 8, REDUCE0>(v, ta, q, two_q, zero);
+    tmem_wait_ld16(tb);
+    tmem_ld16(taddr + 64, ta);
+    gs_blocks<0, 24, 8, REDUCE0>(v, tb, q, two_q, zero);
+    tmem_wait_ld16(ta);
+    tmem_ld16(taddr + 80, tb);
+    gs_blocks<1, 0, 8, true>(v, ta, q, two_q, zero);
+    tmem_wait_ld16(tb);
+    tmem_ld16(taddr + 96, ta);
+    gs_blocks<1, 8, 8, true>(v, tb, q, two_q, zero);
+    tmem_wait_ld16(ta);
+    tmem_ld16(taddr + 112, tb);
+    gs_blocks<2, 0, 8, true>(v, ta, q, two_q, zero);
+    tmem_wait_ld16(tb);
+    gs_blocks<3, 0, 4, true>(v, tb, q, two_q, zero);
+    gs_blocks<4, 0, 2, true>(v, tb + 8, q, two_q, zero);
+    gs_blocks<5, 0, 1, true>(v, tb + 12, q, two_q, zero);
+}
+
+// CT stages 5..0 (stride 32 -> 1 inside the thread's 64 contiguous coefficients), same table
+template <bool REDUCE_FIRST>
+__device__ __forceinline__ void ct_round_tmem(uint32_t (&v)[64], uint32_t taddr, uint32_t q,
+                                              uint32_t two_q, uint32_t zero) {
+    uint32_t ta[16], tb[16];
+    tmem_ld16(taddr + 112, tb);
+    tmem_wait_ld16(tb);
+    tmem_ld16(taddr + 96, ta);
+    ct_blocks<5, 0, 1, REDUCE_FIRST>(v, tb + 12, q, two_q, zero);
+    ct_blocks<4, 0, 2, true>(v, tb + 8, q, two_q, zero);
+    ct_blocks<3, 0, 4, true>(v, tb, q, two_q, zero);
+    tmem_wait_ld16(ta);
+    tmem_ld16(taddr + 80, tb);
+    ct_blocks<2, 0, 8, true>(v, ta, q, two_q, zero);
+    tmem_wait_ld16(tb);
+    tmem_ld16(taddr + 64, ta);
+    ct_blocks<1, 8, 8, true>(v, tb, q, two_q, zero);
+    tmem_wait_ld16(ta);
+    tmem_ld16(taddr + 48, tb);
+    ct_blocks<1, 0, 8, true>(v, ta, q, two_q, zero);
+    tmem_wait_ld16(tb);
+    tmem_ld16(taddr + 32, ta);
+    ct_blocks<0, 24, 8, true>(v, tb, q, two_q, zero);
+    tmem_wait_ld16(ta);
+    tmem_ld16(taddr + 16, tb);
+    ct_blocks<0, 16, 8, true>(v, ta, q, two_q, zero);
+    tmem_wait_ld16(tb);
+    tmem_ld16(taddr, ta);
+    ct_blocks<0, 8, 8, true>(v, tb, q, two_q, zero);
+    tmem_wait_ld16(ta);
+    ct_blocks<0, 0, 8, true>(v, ta, q, two_q, zero);
+}
+
 }  // namespace nttb200

@@ -26,6 +26,7 @@
 // src/aie2.py:161-317; the twiddle index rule is the golden's table[h+i]
 // (src/test.cpp:45).
 #include <cuda.h>
+#include <stdlib.h>
 
 #include <vector>
 
@@ -114,7 +115,9 @@ struct FusedParams {
     uint32_t scale_shoup; // N^-1 of an inverse transform, fused into the store
 };
 
-template <bool PERMUTE, bool SCALE = false>
+// TWTMEM: the round-1 private twiddles live in tensor memory (128 columns, lanes = threads)
+// instead of the 32 KiB shared-memory table.
+template <bool PERMUTE, bool SCALE = false, bool LOCKSTEP = false, bool TWTMEM = false>
 __global__ void __launch_bounds__(kF_Threads, 1)
 fused_gs4096_kernel(const __grid_constant__ CUtensorMap map_lo,
                     const __grid_constant__ CUtensorMap map_hi,
@@ -135,13 +138,42 @@ fused_gs4096_kernel(const __grid_constant__ CUtensorMap map_lo,
     const uint32_t q = prm.q, two_q = 2u * prm.q, zero = prm.zero;
 
     // stage the round-1 twiddles (kernel-private order, prepared at plan time)
-    for (int i = tid; i < kF_TwSlots * kF_Team; i += kF_Threads) {
-        uint4 t = __ldg(prm.tw_r1 + i);
-        sts128(tw_base + i * 16, t.x, t.y, t.z, t.w);
+    uint32_t tmem_base = 0, tw_taddr = 0;
+    if (TWTMEM) {
+        const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);
+        if (warp == 0) tmem_alloc_512(bar_base + 64);
+        tmem_fence_before_sync();
+        __syncthreads();
+        tmem_fence_after_sync();
+        tmem_base = lds32(bar_base + 64);
+        tw_taddr = tmem_base + ((uint32_t) (warp & 3) << 21);
+        if (warp < 4) {  // teams 0 and 1 cover all 128 lanes
+#pragma unroll 1
+            for (int g = 0; g < 8; g++) {
+                uint32_t r[16];
+#pragma unroll
+                for (int k = 0; k < 4; k++) {
+                    const uint4 x = __ldg(prm.tw_r1 + (size_t) (4 * g + k) * kF_Team + j);
+                    r[4 * k + 0] = x.x;
+                    r[4 * k + 1] = x.y;
+                    r[4 * k + 2] = x.z;
+                    r[4 * k + 3] = x.w;
+                }
+                tmem_st16(tw_taddr + 16u * g, r);
+            }
+            tmem_wait_st();
+        }
+        tmem_fence_before_sync();
+    } else {
+        for (int i = tid; i < kF_TwSlots * kF_Team; i += kF_Threads) {
+            uint4 t = __ldg(prm.tw_r1 + i);
+            sts128(tw_base + i * 16, t.x, t.y, t.z, t.w);
+        }
     }
     if (tid < kF_Teams) mbar_init(bar_base + tid * 8, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     __syncthreads();
+    if (TWTMEM) tmem_fence_after_sync();
 
     const uint32_t buf = data_base + team * kF_PolyBytes;
     const uint32_t bar = bar_base + team * 8;
@@ -178,12 +210,16 @@ fused_gs4096_kernel(const __grid_constant__ CUtensorMap map_lo,
             v[4 * c + 2] = t.z;
             v[4 * c + 3] = t.w;
         }
-        round1_stage<0>(v, tw_addr, q, two_q, zero);
-        round1_stage<1>(v, tw_addr, q, two_q, zero);
-        round1_stage<2>(v, tw_addr, q, two_q, zero);
-        round1_stage<3>(v, tw_addr, q, two_q, zero);
-        round1_stage<4>(v, tw_addr, q, two_q, zero);
-        round1_stage<5>(v, tw_addr, q, two_q, zero);
+        if (TWTMEM) {
+            gs_round_tmem<false>(v, tw_taddr, q, two_q, zero);
+        } else {
+            round1_stage<0>(v, tw_addr, q, two_q, zero);
+            round1_stage<1>(v, tw_addr, q, two_q, zero);
+            round1_stage<2>(v, tw_addr, q, two_q, zero);
+            round1_stage<3>(v, tw_addr, q, two_q, zero);
+            round1_stage<4>(v, tw_addr, q, two_q, zero);
+            round1_stage<5>(v, tw_addr, q, two_q, zero);
+        }
 
         // ---- exchange through the same buffer (row write, column read)
 #pragma unroll
@@ -191,13 +227,13 @@ fused_gs4096_kernel(const __grid_constant__ CUtensorMap map_lo,
             sts128(r1_row + (c >> 3) * (kF_PolyBytes / 2) + (((c & 7) << 4) ^ r1_xor), v[4 * c],
                    v[4 * c + 1], v[4 * c + 2], v[4 * c + 3]);
         }
-        team_sync(team);
+        if (LOCKSTEP) __syncthreads(); else team_sync(team);
 #pragma unroll
         for (int i = 0; i < 64; i++) {
             v[i] = lds32(r2_col + i * 128 + (r2_chunk ^ ((i & 7) << 4)));
         }
         fence_proxy_async();
-        team_sync(team);
+        if (LOCKSTEP) __syncthreads(); else team_sync(team);
 
         // ---- the buffer is free: prefetch this team's next polynomial
         const uint64_t next = poly + stride;
@@ -232,6 +268,11 @@ fused_gs4096_kernel(const __grid_constant__ CUtensorMap map_lo,
                 dst[row * 64] = v[i];
             }
         }
+    }
+    if (TWTMEM) {
+        tmem_fence_before_sync();
+        __syncthreads();
+        if (tid < 32) tmem_dealloc_512(tmem_base);
     }
 }
 
@@ -313,6 +354,10 @@ int fused_prepare(nttb200_plan *p) {
                                       cudaFuncAttributeMaxDynamicSharedMemorySize, kF_SmemBytes));
     NTTB200_CUDA(cudaFuncSetAttribute(fused_gs4096_kernel<false, true>,
                                       cudaFuncAttributeMaxDynamicSharedMemorySize, kF_SmemBytes));
+    NTTB200_CUDA(cudaFuncSetAttribute(fused_gs4096_kernel<false, false, true>,
+                                      cudaFuncAttributeMaxDynamicSharedMemorySize, kF_SmemBytes));
+    NTTB200_CUDA(cudaFuncSetAttribute(fused_gs4096_kernel<false, false, false, true>,
+                                      cudaFuncAttributeMaxDynamicSharedMemorySize, kF_SmemBytes));
     return NTTB200_OK;
 }
 
@@ -369,6 +414,12 @@ static int launch_fused_impl(nttb200_plan *p, const int32_t *d_in, int32_t *d_ou
     } else if (permute_out) {
         fused_gs4096_kernel<true><<<grid, kF_Threads, kF_SmemBytes, st>>>(map_lo, map_hi, p->uni_gs,
                                                                           prm);
+    } else if (getenv("NTTB200_FUSED_TMEM")) {
+        fused_gs4096_kernel<false, false, false, true><<<grid, kF_Threads, kF_SmemBytes, st>>>(
+            map_lo, map_hi, p->uni_gs, prm);
+    } else if (getenv("NTTB200_FUSED_LOCKSTEP") && batch % kF_Teams == 0) {
+        fused_gs4096_kernel<false, false, true><<<grid, kF_Threads, kF_SmemBytes, st>>>(
+            map_lo, map_hi, p->uni_gs, prm);
     } else {
         fused_gs4096_kernel<false><<<grid, kF_Threads, kF_SmemBytes, st>>>(map_lo, map_hi,
                                                                            p->uni_gs, prm);

@@ -79,6 +79,11 @@ int build_generated_table(nttb200_plan *p, uint32_t kind, uint32_t base, uint32_
 int build_tile_table(nttb200_plan *p);
 int launch_reduce(nttb200_plan *p, const int32_t *in, int32_t *out, size_t count, cudaStream_t st);
 
+// one-kernel negacyclic product, N = 4096 (kernels_polymul.cu)
+int polymul_prepare();
+int launch_polymul4096(nttb200_plan *fwd, nttb200_plan *inv, const int32_t *d_a, const int32_t *d_b,
+                       int32_t *d_c, size_t batch, cudaStream_t st);
+
 // generic stage-pass kernels (kernels_generic.cu): stages [sb, se) of the GS
 // (ascending stride) or CT (descending stride) network; permute_out applies the
 // ans_order block permutation on the last pass's store.

@@ -717,3 +717,44 @@ def test_stage_range_empty_batch_and_scatter_limits(lib):
         plan.gs_stage_range(0, 0, 0, 0, 14)
         plan.gs(0, 0, 0)
         plan.ct(0, 0, 0)
+
+
+def test_polymul4096_one_kernel(lib, oracle_mod):
+    """N = 4096 products in ONE kernel (operands parked in tensor memory): ragged batches
+    around the team/grid sizes, three moduli (29-bit, 30-bit, 16-bit), output aliasing a or
+    b, against the oracle pipeline CT, CT, pointwise, GS, N^-1 and one schoolbook row."""
+    n = 4096
+    rng = np.random.default_rng(20000)
+    for q in (Q29, _ntt_primes(1)[0], 40961):
+        psi = _psi(n, q)
+        fwd = lib.make_bitrev_table(n, q, psi)
+        inv = lib.make_bitrev_table(n, q, pow(psi, q - 2, q))
+        big = 1190 if q == Q29 else 19
+        a = rng.integers(0, q, (big, n), dtype=np.int32)
+        b = rng.integers(0, q, (big, n), dtype=np.int32)
+        a[0] = q - 1
+        b[0] = q - 1
+        a[1] = 0
+        prod = oracle_mod.pointwise(oracle_mod.ntt_ct(a, fwd, q), oracle_mod.ntt_ct(b, fwd, q), q)
+        want = oracle_mod.scale(oracle_mod.ntt_gs(prod, inv, q), oracle_mod.powmod(n, q - 2, q), q)
+        assert np.array_equal(want[2], oracle_mod.negacyclic_schoolbook(a[2], b[2], q))
+        with lib.Plan(12, q, fwd) as pf, lib.Plan(12, q, inv) as pi:
+            for batch in (1, 7, 8, 9, big):
+                d_a, d_b = dev(a[:batch]), dev(b[:batch])
+                d_c = torch.zeros_like(d_a)
+                lib.polymul_negacyclic(pf, pi, d_a, d_b, d_c, batch)
+                assert "one_kernel" in pi.last_path, pi.last_path
+                assert np.array_equal(d_c.cpu().numpy(), want[:batch]), (q, batch)
+                assert np.array_equal(d_a.cpu().numpy(), a[:batch])
+                assert np.array_equal(d_b.cpu().numpy(), b[:batch])
+                lib.polymul_negacyclic(pf, pi, d_a, d_b, d_a, batch)      # c aliases a
+                assert np.array_equal(d_a.cpu().numpy(), want[:batch]), (q, batch, "alias a")
+                d_a = dev(a[:batch])
+                lib.polymul_negacyclic(pf, pi, d_a, d_b, d_b, batch)      # c aliases b
+                assert np.array_equal(d_b.cpu().numpy(), want[:batch]), (q, batch, "alias b")
+            # twice in a row on one stream (TMEM is allocated and released per launch)
+            d_a, d_b = dev(a), dev(b)
+            d_c = torch.zeros_like(d_a)
+            for _ in range(3):
+                lib.polymul_negacyclic(pf, pi, d_a, d_b, d_c, big)
+            assert np.array_equal(d_c.cpu().numpy(), want)
