@@ -30,144 +30,9 @@
 
 #include <vector>
 
-#include "fused_common.cuh"
-#include "plan.h"
+#include "tile_common.cuh"
 
 namespace nttb200 {
-
-constexpr int kM_Teams = 8;
-constexpr int kM_Threads = kF_Team * kM_Teams;
-constexpr int kM_TwRow = 65;                    // 64 round-1 threads + 1 round-2 entry
-constexpr int kM_TwTile = 32 * kM_TwRow;        // uint4s of twiddles per tile position
-constexpr int kM_SmemBytes = kM_Teams * kF_PolyBytes + 64 + 1024;
-
-__device__ __forceinline__ uint4 ldg128(const uint4 *p) { return __ldg(p); }
-
-// Where a team's twiddle slots come from: global memory (LDG, L1-resident across a
-// batch) or -- when every tile uses the same table (N = 4096) -- a shared-memory copy.
-struct TwGlobal {
-    const uint4 *p;
-    __device__ __forceinline__ uint4 slot(int s) const { return ldg128(p + s * 65); }
-};
-struct TwShared {
-    uint32_t addr;
-    __device__ __forceinline__ uint4 slot(int s) const { return lds128(addr + s * (65 * 16)); }
-};
-
-// One stage on the thread's 64 registers (pairs i, i + 2^S); the two (w, w') pairs of
-// blocks b, b+1 come as one uint4 from tw[slot * 65] (slot = 0,16,24,28,30,31 + b/2).
-template <int S, bool REDUCE, class TW>
-__device__ __forceinline__ void gs_stage_t(uint32_t (&v)[64], const TW tw, uint32_t q,
-                                           uint32_t two_q, uint32_t zero) {
-    constexpr int kBlocks = 32 >> S;
-    constexpr int kSlot0 = 32 - (kBlocks >= 2 ? kBlocks : 1);
-    constexpr int kStride = 1 << S;
-#pragma unroll
-    for (int b = 0; b < kBlocks; b += 2) {
-        uint4 t = tw.slot(kSlot0 + b / 2);
-#pragma unroll
-        for (int e = 0; e < kStride; e++) {
-            int i0 = b * 2 * kStride + e;
-            gs_bfly<REDUCE>(v[i0], v[i0 + kStride], t.x, t.y, q, two_q, zero);
-        }
-        if (kBlocks >= 2) {
-#pragma unroll
-            for (int e = 0; e < kStride; e++) {
-                int i0 = (b + 1) * 2 * kStride + e;
-                gs_bfly<REDUCE>(v[i0], v[i0 + kStride], t.z, t.w, q, two_q, zero);
-            }
-        }
-    }
-}
-
-
-// CT stage on the thread's 64 registers (pairs i, i + 2^S), same twiddle slots as GS
-template <int S, bool REDUCE_X, class TW>
-__device__ __forceinline__ void ct_stage_t(uint32_t (&v)[64], const TW tw, uint32_t q,
-                                           uint32_t two_q, uint32_t zero) {
-    constexpr int kBlocks = 32 >> S;
-    constexpr int kSlot0 = 32 - (kBlocks >= 2 ? kBlocks : 1);
-    constexpr int kStride = 1 << S;
-#pragma unroll
-    for (int b = 0; b < kBlocks; b += 2) {
-        uint4 t = tw.slot(kSlot0 + b / 2);
-#pragma unroll
-        for (int e = 0; e < kStride; e++) {
-            int i0 = b * 2 * kStride + e;
-            ct_bfly<REDUCE_X>(v[i0], v[i0 + kStride], t.x, t.y, q, two_q, zero);
-        }
-        if (kBlocks >= 2) {
-#pragma unroll
-            for (int e = 0; e < kStride; e++) {
-                int i0 = (b + 1) * 2 * kStride + e;
-                ct_bfly<REDUCE_X>(v[i0], v[i0 + kStride], t.z, t.w, q, two_q, zero);
-            }
-        }
-    }
-}
-
-template <int S, bool REDUCE>
-__device__ __forceinline__ void gs_stage_g(uint32_t (&v)[64], const uint4 *tw, uint32_t q,
-                                           uint32_t two_q, uint32_t zero) {
-    gs_stage_t<S, REDUCE>(v, TwGlobal{tw}, q, two_q, zero);
-}
-template <int S, bool REDUCE_X>
-__device__ __forceinline__ void ct_stage_g(uint32_t (&v)[64], const uint4 *tw, uint32_t q,
-                                           uint32_t two_q, uint32_t zero) {
-    ct_stage_t<S, REDUCE_X>(v, TwGlobal{tw}, q, two_q, zero);
-}
-
-template <bool REDUCE0, class TW>
-__device__ __forceinline__ void gs_round(uint32_t (&v)[64], const TW tw, uint32_t q, uint32_t two_q,
-                                         uint32_t zero) {
-    gs_stage_t<0, REDUCE0>(v, tw, q, two_q, zero);
-    gs_stage_t<1, true>(v, tw, q, two_q, zero);
-    gs_stage_t<2, true>(v, tw, q, two_q, zero);
-    gs_stage_t<3, true>(v, tw, q, two_q, zero);
-    gs_stage_t<4, true>(v, tw, q, two_q, zero);
-    gs_stage_t<5, true>(v, tw, q, two_q, zero);
-}
-template <bool REDUCE_FIRST, class TW>
-__device__ __forceinline__ void ct_round(uint32_t (&v)[64], const TW tw, uint32_t q, uint32_t two_q,
-                                         uint32_t zero) {
-    ct_stage_t<5, REDUCE_FIRST>(v, tw, q, two_q, zero);
-    ct_stage_t<4, true>(v, tw, q, two_q, zero);
-    ct_stage_t<3, true>(v, tw, q, two_q, zero);
-    ct_stage_t<2, true>(v, tw, q, two_q, zero);
-    ct_stage_t<1, true>(v, tw, q, two_q, zero);
-    ct_stage_t<0, true>(v, tw, q, two_q, zero);
-}
-
-// CT stage K on registers that pair rows i and i + 2^K of one column, twiddles that do not
-// depend on the thread (table[(32 >> K) + block]) straight from the constant bank
-template <int K, bool REDUCE_X>
-__device__ __forceinline__ void ct_stage_uniform(uint32_t (&v)[64], const UniformTw &u, uint32_t q,
-                                                 uint32_t two_q, uint32_t zero) {
-    constexpr int kStride = 1 << K;
-#pragma unroll
-    for (int b = 0; b < (32 >> K); b++) {
-        const uint32_t w = u.w[(32 >> K) + b], wp = u.wp[(32 >> K) + b];
-#pragma unroll
-        for (int e = 0; e < kStride; e++) {
-            int i0 = b * 2 * kStride + e;
-            ct_bfly<REDUCE_X>(v[i0], v[i0 + kStride], w, wp, q, two_q, zero);
-        }
-    }
-}
-
-constexpr int kM_SmemBytesTw = kM_SmemBytes + kM_TwTile * 16;  // + one shared twiddle table
-
-struct TileParams {
-    uint32_t *out;
-    const uint4 *tw_tile;  // [chunks][32][65]
-    uint32_t batch;
-    uint32_t chunks;       // tiles per polynomial
-    uint32_t q;
-    uint32_t zero;
-    uint32_t qinv;         // q^-1 mod 2^32 (DUAL: Montgomery product of the two inputs)
-    uint32_t scale;        // DUAL: every output is multiplied by this constant (Shoup pair)
-    uint32_t scale_shoup;
-};
 
 // RNS: tile position c = residue-channel index, each with its own modulus:
 // pos[c] = (q_c, q_c^-1 mod 2^32, scale_c, scale_c's Shoup companion).  Passed as a kernel
@@ -1148,6 +1013,16 @@ int multi_prepare(nttb200_plan *p) {
     int rc = build_tile_table(p);
     if (rc != NTTB200_OK) return rc;
     NTTB200_CUDA(cudaDeviceSynchronize());
+    if (p->logn >= 13) {
+        uint2 head[16];
+        NTTB200_CUDA(cudaMemcpy(head, p->d_tw, sizeof(head), cudaMemcpyDeviceToHost));
+        for (int i = 0; i < 16; i++) {
+            p->cross_tw.w[i] = head[i].x;
+            p->cross_tw.wp[i] = head[i].y;
+        }
+    }
+    rc = polyt_prepare();
+    if (rc != NTTB200_OK) return rc;
     return multi_set_attrs();
 }
 
@@ -1352,7 +1227,9 @@ int launch_multi_gs(nttb200_plan *p, const int32_t *d_in, int32_t *d_out, size_t
     // pass writes is still in the 126 MB L2 when the column pass reads it, so the
     // intermediate never costs HBM bandwidth.
     {
-        int rc = launch_poly_gs(p, d_in, nullptr, d_out, batch, st);
+        int rc = launch_polyt_gs(p, d_in, nullptr, d_out, batch, st);
+        if (rc != NTTB200_ERR_UNSUPPORTED) return rc;
+        rc = launch_poly_gs(p, d_in, nullptr, d_out, batch, st);
         if (rc == NTTB200_OK) p->last_path = "poly_tma_3round";
         if (rc != NTTB200_ERR_UNSUPPORTED) return rc;
     }
@@ -1445,7 +1322,9 @@ int launch_multi_gs_dual(nttb200_plan *p, const int32_t *d_a, const int32_t *d_b
         return NTTB200_ERR_UNSUPPORTED;
     }
     if (batch == 0) return NTTB200_OK;
-    int rc = launch_poly_gs(p, d_a, d_b, d_out, batch, st);
+    int rc = launch_polyt_gs(p, d_a, d_b, d_out, batch, st);
+    if (rc != NTTB200_ERR_UNSUPPORTED) return rc;
+    rc = launch_poly_gs(p, d_a, d_b, d_out, batch, st);
     if (rc == NTTB200_OK) p->last_path = "poly_tma_3round_dual";
     if (rc != NTTB200_ERR_UNSUPPORTED) return rc;
     rc = launch_multi_gs_once(p, d_a, d_b, d_out, batch, st);
@@ -1471,6 +1350,10 @@ int launch_multi_ct_mul(nttb200_plan *p, const int32_t *d_in, const int32_t *d_m
     }
     if (batch == 0) return NTTB200_OK;
     const int logg = (int) p->logn - 12;
+    if (!d_mul) {
+        int rc = launch_polyt_ct(p, d_in, d_out, batch, st);
+        if (rc != NTTB200_ERR_UNSUPPORTED) return rc;
+    }
     if (logg >= 1 && logg <= 3 && poly_kernel_enabled()) {
         // N = 2^13..2^15: one pass, cross-tile stages inside the CTA
         const uint64_t ptiles = (uint64_t) batch << logg;

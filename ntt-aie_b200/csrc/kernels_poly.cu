@@ -1,0 +1,494 @@
+// kernels_poly.cu -- N = 2^13 .. 2^15 in ONE pass with every private twiddle in tensor memory.
+//
+// As poly_gs_kernel / poly_ct_kernel of kernels_multi.cu: the G = N/4096 tiles of a
+// polynomial are taken by G teams of one CTA at the same time, two register rounds per
+// tile (stages 0-11) and a third round through the tile buffers for the log2 G cross-tile
+// stages -- one HBM read + one write per coefficient.  The successor of the reference's
+// tile-local stages followed by cross-tile ntt_1stage calls (src/aie_core.cc:161-361,
+// src/aie2.py:178-295).
+//
+// What changed against the first version: there a tile position's 4032 private (w, w')
+// pairs were fetched with LDG.128 on the critical path (G x 33 KiB per CTA does not fit
+// L1 next to 132 KiB of shared memory: 41 % hit rate, long-scoreboard stalls, issue slots
+// 51 % busy -- profiles/r1_secondary_kernels_ncu.txt).  Here each position's table sits in
+// TENSOR MEMORY: 128 columns per table, lanes = threads; positions of equal parity share a
+// lane half, so G = 8 fills exactly the 512 columns.  Round-2 pairs (63 per position) are
+// staged in shared memory, the G-1 cross-tile pairs travel as kernel parameters (constant
+// bank).  After the prologue the kernel touches global memory for data only.
+#include <cuda.h>
+#include <stdlib.h>
+
+#include "tile_common.cuh"
+
+namespace nttb200 {
+
+constexpr int kY_SmemBytes = kM_Teams * kF_PolyBytes + 128 + 8 * 512 + 1024;
+
+struct Tw16 {               // round-2 pairs of one position in shared memory: 32 uint4 slots
+    uint32_t addr;
+    __device__ __forceinline__ uint4 slot(int s) const { return lds128(addr + s * 16); }
+};
+
+// prologue shared by both kernels: TMEM allocation, mbarriers, round-2 tables to shared
+// memory, private tables to tensor memory.  Returns this thread's lane base address.
+template <int G>
+__device__ __forceinline__ uint32_t poly_prologue(const uint4 *tw_tile, uint32_t bar_base, int tid,
+                                                  int warp, int j, uint32_t &tmem_base) {
+    const uint32_t tmem_slot = bar_base + 64, r2base = bar_base + 128;
+    if (warp == 0) tmem_alloc_512(tmem_slot);
+    if (tid < kM_Teams) mbar_init(bar_base + tid * 8, 1);
+    for (int i = tid; i < G * 32; i += kM_Threads) {
+        const uint4 x = __ldg(tw_tile + (size_t) (i >> 5) * kM_TwTile + (i & 31) * kM_TwRow + 64);
+        sts128(r2base + i * 16, x.x, x.y, x.z, x.w);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    tmem_fence_before_sync();
+    __syncthreads();
+    tmem_fence_after_sync();
+    tmem_base = lds32(tmem_slot);
+    const uint32_t lane_base = tmem_base + ((uint32_t) (warp & 3) << 21);
+    if (warp < 4) {  // teams 0 and 1 cover all 128 lanes; lane half h holds positions of parity h
+#pragma unroll 1
+        for (int pos = warp >> 1; pos < G; pos += 2) {
+            const uint4 *src = tw_tile + (size_t) pos * kM_TwTile + j;
+#pragma unroll 1
+            for (int g = 0; g < 8; g++) {
+                uint32_t r[16];
+#pragma unroll
+                for (int k = 0; k < 4; k++) {
+                    const uint4 x = __ldg(src + (4 * g + k) * kM_TwRow);
+                    r[4 * k + 0] = x.x;
+                    r[4 * k + 1] = x.y;
+                    r[4 * k + 2] = x.z;
+                    r[4 * k + 3] = x.w;
+                }
+                tmem_st16(lane_base + (uint32_t) (pos >> 1) * 128u + 16u * g, r);
+            }
+        }
+        tmem_wait_st();
+    }
+    tmem_fence_before_sync();
+    __syncthreads();
+    tmem_fence_after_sync();
+    return lane_base;
+}
+
+template <int LOGG, bool DUAL>
+__global__ void __launch_bounds__(kM_Threads, 1)
+polyt_gs_kernel(const __grid_constant__ CUtensorMap map_lo, const __grid_constant__ CUtensorMap map_hi,
+                const __grid_constant__ CUtensorMap map_b_lo,
+                const __grid_constant__ CUtensorMap map_b_hi, const TileParams prm,
+                const __grid_constant__ CrossTw cross) {
+    constexpr int G = 1 << LOGG;           // tiles = teams per polynomial
+    constexpr int kGroups = kM_Teams / G;  // polynomials in flight per CTA
+    constexpr int kSlice = 64 / G;         // register rows a thread keeps in round 3
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t data_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    const uint32_t bar_base = data_base + kM_Teams * kF_PolyBytes;
+    const int tid = threadIdx.x;
+    const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);
+    const int team = warp >> 1;
+    const int j = tid & 63;
+    const int grp = team >> LOGG, t = team & (G - 1);
+    const uint32_t q = prm.q, two_q = 2u * prm.q, zero = prm.zero;
+
+    uint32_t tmem_base;
+    const uint32_t lane_base = poly_prologue<G>(prm.tw_tile, bar_base, tid, warp, j, tmem_base);
+    const uint32_t tw1 = lane_base + (uint32_t) (t >> 1) * 128u;   // team parity == position parity
+    const Tw16 tw2{bar_base + 128 + (uint32_t) t * 512u};
+
+    const uint32_t buf = data_base + team * kF_PolyBytes;
+    const uint32_t gbuf = data_base + (grp << LOGG) * kF_PolyBytes;
+    const uint32_t bar = bar_base + team * 8;
+    const uint32_t stride = gridDim.x * kGroups;
+    uint32_t poly = blockIdx.x * kGroups + grp;
+    uint32_t parity = 0;
+    if (j == 0 && poly < prm.batch) {
+        mbar_expect_tx(bar, kF_PolyBytes);
+        tma_load_3d(buf, &map_lo, bar, 0, 0, (int) (poly * G + t));
+        tma_load_3d(buf + kF_PolyBytes / 2, &map_hi, bar, 0, 0, (int) (poly * G + t));
+    }
+    const uint32_t r1_row = buf + j * 128;
+    const uint32_t r1_xor = (j & 7) << 4;
+    const uint32_t r2_col = buf + (j >> 5) * (kF_PolyBytes / 2) + (j & 3) * 4;
+    const uint32_t r2_chunk = ((j & 31) >> 2) << 4;
+    auto group_sync = [&]() {
+        asm volatile("bar.sync %0, %1;" ::"r"(9 + grp), "n"(G * 64) : "memory");
+    };
+
+    for (; poly < prm.batch; poly += stride) {
+        uint32_t v[64];
+        const int tile = (int) (poly * G + t);
+        mbar_wait(bar, parity);
+        parity ^= 1;
+#pragma unroll
+        for (int c = 0; c < 16; c++) {
+            uint4 x = lds128(r1_row + (c >> 3) * (kF_PolyBytes / 2) + (((c & 7) << 4) ^ r1_xor));
+            v[4 * c + 0] = x.x;
+            v[4 * c + 1] = x.y;
+            v[4 * c + 2] = x.z;
+            v[4 * c + 3] = x.w;
+        }
+        if (DUAL) {
+            // second operand through the same buffer, then v = a*b*2^-32 mod q in (0, 2q)
+            team_sync(team);
+            if (j == 0) {
+                mbar_expect_tx(bar, kF_PolyBytes);
+                tma_load_3d(buf, &map_b_lo, bar, 0, 0, tile);
+                tma_load_3d(buf + kF_PolyBytes / 2, &map_b_hi, bar, 0, 0, tile);
+            }
+            mbar_wait(bar, parity);
+            parity ^= 1;
+#pragma unroll
+            for (int c = 0; c < 16; c++) {
+                uint4 x = lds128(r1_row + (c >> 3) * (kF_PolyBytes / 2) + (((c & 7) << 4) ^ r1_xor));
+                const uint32_t bb[4] = {x.x, x.y, x.z, x.w};
+#pragma unroll
+                for (int e = 0; e < 4; e++) {
+                    uint64_t prod = (uint64_t) v[4 * c + e] * bb[e];
+                    uint32_t m = (uint32_t) prod * prm.qinv;
+                    v[4 * c + e] = (uint32_t) (prod >> 32) - __umulhi(m, q) + q;
+                }
+            }
+        }
+        // ---- round 1: stages 0..5, private pairs from tensor memory
+        gs_round_tmem<DUAL>(v, tw1, q, two_q, zero);
+#pragma unroll
+        for (int c = 0; c < 16; c++) {
+            sts128(r1_row + (c >> 3) * (kF_PolyBytes / 2) + (((c & 7) << 4) ^ r1_xor), v[4 * c],
+                   v[4 * c + 1], v[4 * c + 2], v[4 * c + 3]);
+        }
+        team_sync(team);
+#pragma unroll
+        for (int i = 0; i < 64; i++) {
+            v[i] = lds32(r2_col + i * 128 + (r2_chunk ^ ((i & 7) << 4)));
+        }
+        team_sync(team);
+        // ---- round 2: stages 6..11, the position's 63 pairs from shared memory
+        gs_round<true>(v, tw2, q, two_q, zero);
+
+        // ---- round 3: register i is a[t*4096 + j + 64 i].  Park it at [i][j] of this
+        // team's buffer, then collect rows t*kSlice .. +kSlice-1 of ALL G tiles.
+#pragma unroll
+        for (int i = 0; i < 64; i++) {
+            asm volatile("st.shared.u32 [%0], %1;" ::"r"(buf + (i * 64 + j) * 4), "r"(v[i]) : "memory");
+        }
+        group_sync();
+        uint32_t w[64];
+#pragma unroll
+        for (int tt = 0; tt < G; tt++) {
+#pragma unroll
+            for (int ii = 0; ii < kSlice; ii++) {
+                w[tt * kSlice + ii] =
+                    lds32(gbuf + tt * kF_PolyBytes + (((t * kSlice + ii) * 64 + j) << 2));
+            }
+        }
+        fence_proxy_async();
+        group_sync();
+        // ---- every buffer of the group is free: prefetch this team's next tile
+        const uint32_t next = poly + stride;
+        if (j == 0 && next < prm.batch) {
+            mbar_expect_tx(bar, kF_PolyBytes);
+            tma_load_3d(buf, &map_lo, bar, 0, 0, (int) (next * G + t));
+            tma_load_3d(buf + kF_PolyBytes / 2, &map_hi, bar, 0, 0, (int) (next * G + t));
+        }
+        // ---- stages 12 .. 12+LOGG-1 pair tiles tt and tt + 2^m; twiddle
+        //      table[(G >> (m+1)) + (tt >> (m+1))], the same for every thread: constant bank
+#pragma unroll
+        for (int m = 0; m < LOGG; m++) {
+#pragma unroll
+            for (int b2 = 0; b2 < (G >> (m + 1)); b2++) {
+                const uint32_t cw = cross.w[(G >> (m + 1)) + b2], cwp = cross.wp[(G >> (m + 1)) + b2];
+#pragma unroll
+                for (int e = 0; e < (1 << m); e++) {
+                    const int t0 = (b2 << (m + 1)) + e;
+#pragma unroll
+                    for (int ii = 0; ii < kSlice; ii++) {
+                        gs_bfly<true>(w[t0 * kSlice + ii], w[(t0 + (1 << m)) * kSlice + ii], cw, cwp, q,
+                                      two_q, zero);
+                    }
+                }
+            }
+        }
+        uint32_t *dst = prm.out + ((size_t) poly << (12 + LOGG)) + j + 64 * (t * kSlice);
+#pragma unroll
+        for (int tt = 0; tt < G; tt++) {
+#pragma unroll
+            for (int ii = 0; ii < kSlice; ii++) {
+                uint32_t r = w[tt * kSlice + ii];
+                if (DUAL) r = shoup_mul_lazy(r, prm.scale, prm.scale_shoup, q);
+                dst[tt * 4096 + ii * 64] = min(r - q, r);
+            }
+        }
+    }
+    tmem_fence_before_sync();
+    __syncthreads();
+    if (warp == 0) tmem_dealloc_512(tmem_base);
+}
+
+// Forward partner: the cross-tile stages come FIRST in the CT order (largest strides),
+// then every team finishes its own tile (columns, exchange, rows) and the rows leave
+// through a TMA store.
+template <int LOGG>
+__global__ void __launch_bounds__(kM_Threads, 1)
+polyt_ct_kernel(const __grid_constant__ CUtensorMap map_lo, const __grid_constant__ CUtensorMap map_hi,
+                const __grid_constant__ CUtensorMap out_lo, const __grid_constant__ CUtensorMap out_hi,
+                const TileParams prm, const __grid_constant__ CrossTw cross) {
+    constexpr int G = 1 << LOGG;
+    constexpr int kGroups = kM_Teams / G;
+    constexpr int kSlice = 64 / G;
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t data_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    const uint32_t bar_base = data_base + kM_Teams * kF_PolyBytes;
+    const int tid = threadIdx.x;
+    const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);
+    const int team = warp >> 1;
+    const int j = tid & 63;
+    const int grp = team >> LOGG, t = team & (G - 1);
+    const uint32_t q = prm.q, two_q = 2u * prm.q, zero = prm.zero;
+
+    uint32_t tmem_base;
+    const uint32_t lane_base = poly_prologue<G>(prm.tw_tile, bar_base, tid, warp, j, tmem_base);
+    const uint32_t tw1 = lane_base + (uint32_t) (t >> 1) * 128u;
+    const Tw16 tw2{bar_base + 128 + (uint32_t) t * 512u};
+
+    const uint32_t buf = data_base + team * kF_PolyBytes;
+    const uint32_t gbuf = data_base + (grp << LOGG) * kF_PolyBytes;
+    const uint32_t bar = bar_base + team * 8;
+    const uint32_t stride = gridDim.x * kGroups;
+    uint32_t poly = blockIdx.x * kGroups + grp;
+    uint32_t parity = 0;
+    if (j == 0 && poly < prm.batch) {
+        mbar_expect_tx(bar, kF_PolyBytes);
+        tma_load_3d(buf, &map_lo, bar, 0, 0, (int) (poly * G + t));
+        tma_load_3d(buf + kF_PolyBytes / 2, &map_hi, bar, 0, 0, (int) (poly * G + t));
+    }
+    const uint32_t r1_row = buf + j * 128;
+    const uint32_t r1_xor = (j & 7) << 4;
+    const uint32_t col_off = (j >> 5) * (kF_PolyBytes / 2) + (j & 3) * 4;  // column j of a tile buffer
+    const uint32_t r2_col = buf + col_off;
+    const uint32_t r2_chunk = ((j & 31) >> 2) << 4;
+    auto group_sync = [&]() {
+        asm volatile("bar.sync %0, %1;" ::"r"(9 + grp), "n"(G * 64) : "memory");
+    };
+
+    for (; poly < prm.batch; poly += stride) {
+        uint32_t v[64];
+        const int tile = (int) (poly * G + t);
+        mbar_wait(bar, parity);
+        parity ^= 1;
+        group_sync();  // all G tiles of the polynomial are in shared memory
+        // ---- cross-tile stages logn-1 .. 12 on rows t*kSlice .. +kSlice-1 of every tile
+#pragma unroll
+        for (int tt = 0; tt < G; tt++) {
+#pragma unroll
+            for (int ii = 0; ii < kSlice; ii++) {
+                const int i = t * kSlice + ii;  // not a compile-time constant: t is per team
+                v[tt * kSlice + ii] = lds32(gbuf + tt * kF_PolyBytes + col_off + i * 128 +
+                                            (r2_chunk ^ ((i & 7) << 4)));
+            }
+        }
+#pragma unroll
+        for (int mm = 0; mm < LOGG; mm++) {
+            const int m = LOGG - 1 - mm;
+#pragma unroll
+            for (int b2 = 0; b2 < (G >> (m + 1)); b2++) {
+                const uint32_t cw = cross.w[(G >> (m + 1)) + b2], cwp = cross.wp[(G >> (m + 1)) + b2];
+#pragma unroll
+                for (int e = 0; e < (1 << m); e++) {
+                    const int t0 = (b2 << (m + 1)) + e;
+#pragma unroll
+                    for (int ii = 0; ii < kSlice; ii++) {
+                        if (mm == 0) {
+                            ct_bfly<false>(v[t0 * kSlice + ii], v[(t0 + (1 << m)) * kSlice + ii], cw, cwp,
+                                           q, two_q, zero);
+                        } else {
+                            ct_bfly<true>(v[t0 * kSlice + ii], v[(t0 + (1 << m)) * kSlice + ii], cw, cwp,
+                                          q, two_q, zero);
+                        }
+                    }
+                }
+            }
+        }
+#pragma unroll
+        for (int tt = 0; tt < G; tt++) {
+#pragma unroll
+            for (int ii = 0; ii < kSlice; ii++) {
+                const int i = t * kSlice + ii;
+                asm volatile("st.shared.u32 [%0], %1;" ::"r"(gbuf + tt * kF_PolyBytes + col_off + i * 128 +
+                                                             (r2_chunk ^ ((i & 7) << 4))),
+                             "r"(v[tt * kSlice + ii])
+                             : "memory");
+            }
+        }
+        group_sync();
+        // ---- this team's tile: columns (stages 11..6), exchange, rows (stages 5..0)
+#pragma unroll
+        for (int i = 0; i < 64; i++) {
+            v[i] = lds32(r2_col + i * 128 + (r2_chunk ^ ((i & 7) << 4)));
+        }
+        ct_round<true>(v, tw2, q, two_q, zero);
+#pragma unroll
+        for (int i = 0; i < 64; i++) {
+            asm volatile("st.shared.u32 [%0], %1;" ::"r"(r2_col + i * 128 + (r2_chunk ^ ((i & 7) << 4))),
+                         "r"(v[i])
+                         : "memory");
+        }
+        team_sync(team);
+#pragma unroll
+        for (int c = 0; c < 16; c++) {
+            uint4 x = lds128(r1_row + (c >> 3) * (kF_PolyBytes / 2) + (((c & 7) << 4) ^ r1_xor));
+            v[4 * c + 0] = x.x;
+            v[4 * c + 1] = x.y;
+            v[4 * c + 2] = x.z;
+            v[4 * c + 3] = x.w;
+        }
+        ct_round_tmem<true>(v, tw1, q, two_q, zero);
+#pragma unroll
+        for (int c = 0; c < 16; c++) {
+            uint32_t o[4];
+#pragma unroll
+            for (int e = 0; e < 4; e++) {
+                uint32_t r = v[4 * c + e];
+                r = min(r - two_q, r);
+                o[e] = min(r - q, r);
+            }
+            sts128(r1_row + (c >> 3) * (kF_PolyBytes / 2) + (((c & 7) << 4) ^ r1_xor), o[0], o[1],
+                   o[2], o[3]);
+        }
+        fence_proxy_async();
+        team_sync(team);
+        const uint32_t next = poly + stride;
+        if (j == 0) {
+            tma_store_3d(&out_lo, buf, 0, 0, tile);
+            tma_store_3d(&out_hi, buf + kF_PolyBytes / 2, 0, 0, tile);
+            tma_store_commit_and_wait_read();
+            if (next < prm.batch) {
+                mbar_expect_tx(bar, kF_PolyBytes);
+                tma_load_3d(buf, &map_lo, bar, 0, 0, (int) (next * G + t));
+                tma_load_3d(buf + kF_PolyBytes / 2, &map_hi, bar, 0, 0, (int) (next * G + t));
+            }
+        }
+    }
+    tmem_fence_before_sync();
+    __syncthreads();
+    if (warp == 0) tmem_dealloc_512(tmem_base);
+}
+
+// --------------------------------------------------------------------- host side
+int tile_maps(CUtensorMap *lo, CUtensorMap *hi, const int32_t *base, size_t tiles);  // kernels_fused.cu
+
+int polyt_prepare() {
+    const auto attr = cudaFuncAttributeMaxDynamicSharedMemorySize;
+    NTTB200_CUDA(cudaFuncSetAttribute(polyt_gs_kernel<1, false>, attr, kY_SmemBytes));
+    NTTB200_CUDA(cudaFuncSetAttribute(polyt_gs_kernel<2, false>, attr, kY_SmemBytes));
+    NTTB200_CUDA(cudaFuncSetAttribute(polyt_gs_kernel<3, false>, attr, kY_SmemBytes));
+    NTTB200_CUDA(cudaFuncSetAttribute(polyt_gs_kernel<1, true>, attr, kY_SmemBytes));
+    NTTB200_CUDA(cudaFuncSetAttribute(polyt_gs_kernel<2, true>, attr, kY_SmemBytes));
+    NTTB200_CUDA(cudaFuncSetAttribute(polyt_gs_kernel<3, true>, attr, kY_SmemBytes));
+    NTTB200_CUDA(cudaFuncSetAttribute(polyt_ct_kernel<1>, attr, kY_SmemBytes));
+    NTTB200_CUDA(cudaFuncSetAttribute(polyt_ct_kernel<2>, attr, kY_SmemBytes));
+    NTTB200_CUDA(cudaFuncSetAttribute(polyt_ct_kernel<3>, attr, kY_SmemBytes));
+    return NTTB200_OK;
+}
+
+static uint32_t py_inv_mod_2_32(uint32_t q) {  // q odd
+    uint32_t x = q;
+    for (int i = 0; i < 5; i++) x *= 2u - q * x;
+    return x;
+}
+
+static bool polyt_enabled() {
+    static const bool on = getenv("NTTB200_POLY_NO_TMEM") == nullptr;
+    return on;
+}
+
+template <int LOGG, bool DUAL>
+static void polyt_gs_launch(int grid, cudaStream_t st, const CUtensorMap &a_lo, const CUtensorMap &a_hi,
+                            const CUtensorMap &b_lo, const CUtensorMap &b_hi, const TileParams &tp,
+                            const CrossTw &cross) {
+    polyt_gs_kernel<LOGG, DUAL><<<grid, kM_Threads, kY_SmemBytes, st>>>(a_lo, a_hi, b_lo, b_hi, tp, cross);
+}
+
+// N = 2^13..2^15 golden network in one pass.  d_b != nullptr: input = d_in (*) d_b (Montgomery
+// product), output scaled by N^-1 * 2^32 -- the tail of a negacyclic multiplication.
+int launch_polyt_gs(nttb200_plan *p, const int32_t *d_in, const int32_t *d_b, int32_t *d_out,
+                    size_t batch, cudaStream_t st) {
+    const int logg = (int) p->logn - 12;
+    if (logg < 1 || logg > 3 || !p->d_tw_tile || !polyt_enabled()) return NTTB200_ERR_UNSUPPORTED;
+    const uint64_t tiles = (uint64_t) batch << logg;
+    if (tiles > 0x7fffffffull) return NTTB200_ERR_UNSUPPORTED;
+    CUtensorMap a_lo, a_hi, b_lo, b_hi;
+    if (tile_maps(&a_lo, &a_hi, d_in, (size_t) tiles) != NTTB200_OK) return NTTB200_ERR_UNSUPPORTED;
+    TileParams tp;
+    tp.out = reinterpret_cast<uint32_t *>(d_out);
+    tp.tw_tile = p->d_tw_tile;
+    tp.batch = (uint32_t) batch;
+    tp.chunks = p->n >> 12;
+    tp.q = p->q;
+    tp.zero = 0;
+    tp.qinv = tp.scale = tp.scale_shoup = 0;
+    if (d_b) {
+        if (tile_maps(&b_lo, &b_hi, d_b, (size_t) tiles) != NTTB200_OK) return NTTB200_ERR_UNSUPPORTED;
+        tp.qinv = py_inv_mod_2_32(p->q);
+        const uint64_t sc = ((uint64_t) p->n_inv << 32) % p->q;
+        tp.scale = (uint32_t) sc;
+        tp.scale_shoup = (uint32_t) ((sc << 32) / p->q);
+    } else {
+        b_lo = a_lo;
+        b_hi = a_hi;
+    }
+    const uint64_t groups = kM_Teams >> logg;
+    const uint64_t ctas = (batch + groups - 1) / groups;
+    const int grid = (int) (ctas < (uint64_t) p->sm_count ? ctas : (uint64_t) p->sm_count);
+    const bool dual = d_b != nullptr;
+    switch (logg * 2 + (dual ? 1 : 0)) {
+        case 2: polyt_gs_launch<1, false>(grid, st, a_lo, a_hi, b_lo, b_hi, tp, p->cross_tw); break;
+        case 3: polyt_gs_launch<1, true>(grid, st, a_lo, a_hi, b_lo, b_hi, tp, p->cross_tw); break;
+        case 4: polyt_gs_launch<2, false>(grid, st, a_lo, a_hi, b_lo, b_hi, tp, p->cross_tw); break;
+        case 5: polyt_gs_launch<2, true>(grid, st, a_lo, a_hi, b_lo, b_hi, tp, p->cross_tw); break;
+        case 6: polyt_gs_launch<3, false>(grid, st, a_lo, a_hi, b_lo, b_hi, tp, p->cross_tw); break;
+        default: polyt_gs_launch<3, true>(grid, st, a_lo, a_hi, b_lo, b_hi, tp, p->cross_tw); break;
+    }
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+    NTTB200_CUDA(cudaGetLastError());
+    p->last_path = dual ? "poly_tmem_3round_dual" : "poly_tmem_3round";
+    return NTTB200_OK;
+}
+
+int launch_polyt_ct(nttb200_plan *p, const int32_t *d_in, int32_t *d_out, size_t batch,
+                    cudaStream_t st) {
+    const int logg = (int) p->logn - 12;
+    if (logg < 1 || logg > 3 || !p->d_tw_tile || !polyt_enabled()) return NTTB200_ERR_UNSUPPORTED;
+    const uint64_t tiles = (uint64_t) batch << logg;
+    if (tiles > 0x7fffffffull) return NTTB200_ERR_UNSUPPORTED;
+    CUtensorMap i_lo, i_hi, o_lo, o_hi;
+    if (tile_maps(&i_lo, &i_hi, d_in, (size_t) tiles) != NTTB200_OK ||
+        tile_maps(&o_lo, &o_hi, d_out, (size_t) tiles) != NTTB200_OK) {
+        return NTTB200_ERR_UNSUPPORTED;
+    }
+    TileParams tp;
+    tp.out = reinterpret_cast<uint32_t *>(d_out);
+    tp.tw_tile = p->d_tw_tile;
+    tp.batch = (uint32_t) batch;
+    tp.chunks = p->n >> 12;
+    tp.q = p->q;
+    tp.zero = 0;
+    tp.qinv = tp.scale = tp.scale_shoup = 0;
+    const uint64_t groups = kM_Teams >> logg;
+    const uint64_t ctas = (batch + groups - 1) / groups;
+    const int grid = (int) (ctas < (uint64_t) p->sm_count ? ctas : (uint64_t) p->sm_count);
+    if (logg == 1) {
+        polyt_ct_kernel<1><<<grid, kM_Threads, kY_SmemBytes, st>>>(i_lo, i_hi, o_lo, o_hi, tp, p->cross_tw);
+    } else if (logg == 2) {
+        polyt_ct_kernel<2><<<grid, kM_Threads, kY_SmemBytes, st>>>(i_lo, i_hi, o_lo, o_hi, tp, p->cross_tw);
+    } else {
+        polyt_ct_kernel<3><<<grid, kM_Threads, kY_SmemBytes, st>>>(i_lo, i_hi, o_lo, o_hi, tp, p->cross_tw);
+    }
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+    NTTB200_CUDA(cudaGetLastError());
+    p->last_path = "poly_tmem_3round_ct";
+    return NTTB200_OK;
+}
+
+}  // namespace nttb200

@@ -22,6 +22,13 @@ struct UniformTw {
     uint32_t wp[64];
 };
 
+// Cross-tile twiddles table[1..15] of the one-pass polynomial kernels (stage 12+m, block b
+// uses entry (G >> (m+1)) + b): kernel parameters = constant-bank operands.
+struct CrossTw {
+    uint32_t w[16];
+    uint32_t wp[16];
+};
+
 }  // namespace nttb200
 
 struct nttb200_plan {
@@ -38,6 +45,7 @@ struct nttb200_plan {
     uint4 *d_tw_r1 = nullptr;        // round-1 per-thread twiddles, kernel-private order
     uint4 *d_tw_tile = nullptr;      // [N/4096][32][65] tile-pass twiddles (logn 12..26)
     nttb200::UniformTw uni_gs{};     // round-2 uniform twiddles, GS network
+    nttb200::CrossTw cross_tw{};     // table[1..15] (logn >= 13)
     int sm_count = 148;
     // written by every launch, possibly from several host threads driving different streams
     std::atomic<const char *> last_path{"none"};
@@ -78,6 +86,13 @@ int build_generated_table(nttb200_plan *p, uint32_t kind, uint32_t base, uint32_
                           uint32_t block_mult);
 int build_tile_table(nttb200_plan *p);
 int launch_reduce(nttb200_plan *p, const int32_t *in, int32_t *out, size_t count, cudaStream_t st);
+
+// N = 2^13..2^15 in one pass, private twiddles in tensor memory (kernels_poly.cu)
+int polyt_prepare();
+int launch_polyt_gs(nttb200_plan *p, const int32_t *d_in, const int32_t *d_b, int32_t *d_out,
+                    size_t batch, cudaStream_t st);
+int launch_polyt_ct(nttb200_plan *p, const int32_t *d_in, int32_t *d_out, size_t batch,
+                    cudaStream_t st);
 
 // one-kernel negacyclic product, N = 4096 (kernels_polymul.cu)
 int polymul_prepare();
