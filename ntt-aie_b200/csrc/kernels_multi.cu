@@ -1022,6 +1022,7 @@ int multi_prepare(nttb200_plan *p) {
         }
     }
     rc = polyt_prepare();
+    if (rc == NTTB200_OK) rc = tilecol_prepare();
     if (rc != NTTB200_OK) return rc;
     return multi_set_attrs();
 }
@@ -1227,7 +1228,9 @@ int launch_multi_gs(nttb200_plan *p, const int32_t *d_in, int32_t *d_out, size_t
     // pass writes is still in the 126 MB L2 when the column pass reads it, so the
     // intermediate never costs HBM bandwidth.
     {
-        int rc = launch_polyt_gs(p, d_in, nullptr, d_out, batch, st);
+        int rc = launch_tilecol_gs(p, d_in, nullptr, d_out, batch, st);
+        if (rc != NTTB200_ERR_UNSUPPORTED) return rc;
+        rc = launch_polyt_gs(p, d_in, nullptr, d_out, batch, st);
         if (rc != NTTB200_ERR_UNSUPPORTED) return rc;
         rc = launch_poly_gs(p, d_in, nullptr, d_out, batch, st);
         if (rc == NTTB200_OK) p->last_path = "poly_tma_3round";
@@ -1322,7 +1325,9 @@ int launch_multi_gs_dual(nttb200_plan *p, const int32_t *d_a, const int32_t *d_b
         return NTTB200_ERR_UNSUPPORTED;
     }
     if (batch == 0) return NTTB200_OK;
-    int rc = launch_polyt_gs(p, d_a, d_b, d_out, batch, st);
+    int rc = launch_tilecol_gs(p, d_a, d_b, d_out, batch, st);
+    if (rc != NTTB200_ERR_UNSUPPORTED) return rc;
+    rc = launch_polyt_gs(p, d_a, d_b, d_out, batch, st);
     if (rc != NTTB200_ERR_UNSUPPORTED) return rc;
     rc = launch_poly_gs(p, d_a, d_b, d_out, batch, st);
     if (rc == NTTB200_OK) p->last_path = "poly_tma_3round_dual";

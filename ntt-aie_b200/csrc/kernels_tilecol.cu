@@ -1,0 +1,461 @@
+// kernels_tilecol.cu -- N = 2^13 .. 2^16 as ONE persistent kernel whose teams are never in
+// lock step: tile items and column items, ordered by counters, intermediate kept in L2.
+//
+// The reference runs a transform as tile-local stages followed by cross-tile stages, with
+// lock-protected fifos between them (src/aie2.py:128-154,178-295; src/aie_core.cc:161-361).
+// The first two GPU designs for N > 4096 were (a) two launches -- tile pass, column pass --
+// which costs a second HBM round trip (N = 2^16: 0.40 of the HBM roofline), and (b) all
+// tiles of a polynomial on the teams of one CTA with a third exchange round, which couples
+// up to 16 warps at CTA-wide barriers (N = 2^15: 0.42; ncu: barrier stalls 1.2 cycles per
+// issue).  Here every team of 64 threads works alone on
+//     T-items  one 4096-coefficient tile: stages 0..11 exactly like the N = 4096 kernel
+//              (TMA in, two register rounds, canonical store), private twiddles of the
+//              tile's position in TENSOR MEMORY;
+//     C-items  the same 1/G slice of all G tiles of one polynomial: 16 x 128-bit loads
+//              (L2 hits: the tiles were written a moment ago), the log2 G cross-tile stages
+//              in registers with constant-bank twiddles, 16 x 128-bit stores;
+// a C-item of polynomial p starts when the G T-items of p have published their stores
+// (per-polynomial counter, release/acquire at GPU scope), and each team defers its C-items
+// by `lag` polynomials so that the wait is practically never taken.  Teams drift freely --
+// no CTA-wide barrier after the prologue -- and every coefficient crosses HBM once in each
+// direction; the intermediate lives in the 126 MB L2 for the few microseconds between the
+// two items.  All CTAs are co-resident (grid <= #SMs, one CTA per SM), which is what makes
+// waiting on another CTA's counter legal.
+//
+// Forward (Cooley-Tukey) partner: the same two item kinds in the opposite order (C-items
+// read the input, T-items finish the tiles: columns, exchange, rows, TMA store).
+#include <cuda.h>
+#include <stdlib.h>
+
+#include "tile_common.cuh"
+
+namespace nttb200 {
+
+constexpr int kTC_SmemBytes = kM_Teams * kF_PolyBytes + 128 + 8 * 512 + 1024;
+constexpr uint32_t kTC_SpinLimit = 1u << 26;   // polls (>= 64 ns each) before a waiter gives up
+
+struct Tw16c {  // round-2 pairs of one position in shared memory: 32 uint4 slots
+    uint32_t addr;
+    __device__ __forceinline__ uint4 slot(int s) const { return lds128(addr + s * 16); }
+};
+
+struct TileColParams {
+    uint32_t *out;
+    const uint4 *tw_tile;  // [G][32][65]
+    uint32_t *done;        // one counter per polynomial, zero at launch
+    uint32_t *error;       // set if a waiter gave up (never in a healthy run)
+    uint32_t batch;
+    uint32_t lag;          // C-items trail the T-items by this many polynomials
+    uint32_t q;
+    uint32_t zero;
+    uint32_t qinv;
+    uint32_t scale;
+    uint32_t scale_shoup;
+};
+
+// Counter reads are RELAXED (LDG.STRONG.GPU): ld.acquire costs an L1 invalidation
+// (CCTL.IVALL) and a CTA fence per read.  The reads of the published data that follow are
+// control-dependent on the value and bypass L1 (ld.global.cg), and the publisher's
+// fence.acq_rel.gpu has pushed its stores to L2 before the increment became visible.
+__device__ __forceinline__ uint32_t ld_counter(const uint32_t *p) {
+    uint32_t v;
+    asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ uint4 ldcg128(const uint32_t *p) {
+    uint4 v;
+    asm volatile("ld.global.cg.v4.u32 {%0, %1, %2, %3}, [%4];"
+                 : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w)
+                 : "l"(p)
+                 : "memory");
+    return v;
+}
+
+// wait until `*ctr >= target` (thread 0 of the team polls; the team barrier that follows
+// orders everybody else behind it)
+__device__ __forceinline__ void wait_counter(const uint32_t *ctr, uint32_t target, uint32_t *error) {
+    uint32_t spins = 0;
+    while (ld_counter(ctr) < target) {
+        __nanosleep(64);
+        if (++spins > kTC_SpinLimit) {
+            atomicExch(error, 1u);
+            break;
+        }
+    }
+}
+
+// ------------------------------------------------------------------ GS (golden network)
+template <int LOGG, bool DUAL>
+__global__ void __launch_bounds__(kM_Threads, 1)
+tilecol_gs_kernel(const __grid_constant__ CUtensorMap map_lo, const __grid_constant__ CUtensorMap map_hi,
+                  const __grid_constant__ CUtensorMap map_b_lo,
+                  const __grid_constant__ CUtensorMap map_b_hi, const TileColParams prm,
+                  const __grid_constant__ CrossTw cross) {
+    constexpr int G = 1 << LOGG;
+    constexpr int H = G > 8 ? 2 : 1;       // CTA classes: 8 position tables fit one CTA's TMEM
+    constexpr int K = G / (2 * H);         // positions per (CTA class, team parity)
+    constexpr int U = 16 / G;              // 128-bit column groups per tile and thread (C-items)
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t data_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    const uint32_t bar_base = data_base + kM_Teams * kF_PolyBytes;
+    const uint32_t tmem_slot = bar_base + 64, r2base = bar_base + 128;
+    const int tid = threadIdx.x;
+    const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);
+    const int team = warp >> 1;
+    const int j = tid & 63;
+    const uint32_t q = prm.q, two_q = 2u * prm.q, zero = prm.zero;
+    const uint32_t cta_half = blockIdx.x & (H - 1);
+    const uint32_t parity_h = team & 1;
+
+    // ---- prologue: TMEM, mbarriers, this CTA's position tables
+    if (warp == 0) tmem_alloc_512(tmem_slot);
+    if (tid < kM_Teams) mbar_init(bar_base + tid * 8, 1);
+    for (int i = tid; i < (G / H) * 32; i += kM_Threads) {   // round-2 pairs: [local position][slot]
+        const uint32_t pos = cta_half * 8 + (i >> 5);
+        const uint4 x = __ldg(prm.tw_tile + (size_t) pos * kM_TwTile + (i & 31) * kM_TwRow + 64);
+        sts128(r2base + i * 16, x.x, x.y, x.z, x.w);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    tmem_fence_before_sync();
+    __syncthreads();
+    tmem_fence_after_sync();
+    const uint32_t tmem_base = lds32(tmem_slot);
+    const uint32_t lane_base = tmem_base + ((uint32_t) (warp & 3) << 21);
+    if (warp < 4) {  // lane half h holds the positions of parity h: columns k*128
+#pragma unroll 1
+        for (int k = 0; k < K; k++) {
+            const uint32_t pos = cta_half * 8 + 2 * k + (warp >> 1);
+            const uint4 *src = prm.tw_tile + (size_t) pos * kM_TwTile + j;
+#pragma unroll 1
+            for (int g = 0; g < 8; g++) {
+                uint32_t r[16];
+#pragma unroll
+                for (int e = 0; e < 4; e++) {
+                    const uint4 x = __ldg(src + (4 * g + e) * kM_TwRow);
+                    r[4 * e + 0] = x.x;
+                    r[4 * e + 1] = x.y;
+                    r[4 * e + 2] = x.z;
+                    r[4 * e + 3] = x.w;
+                }
+                tmem_st16(lane_base + (uint32_t) k * 128u + 16u * g, r);
+            }
+        }
+        tmem_wait_st();
+    }
+    tmem_fence_before_sync();
+    __syncthreads();
+    tmem_fence_after_sync();
+
+    // ---- this team's two work queues
+    const uint32_t class_teams = (gridDim.x / H) * (kM_Teams / 2);
+    const uint32_t t_total = prm.batch * K;                       // T-items of this class
+    uint32_t tq = (blockIdx.x / H) * (kM_Teams / 2) + (team >> 1);
+    const uint32_t num_teams = gridDim.x * kM_Teams;
+    const uint32_t c_total = prm.batch * G;
+    uint32_t cq = blockIdx.x * kM_Teams + team;
+
+    const uint32_t buf = data_base + team * kF_PolyBytes;
+    const uint32_t bar = bar_base + team * 8;
+    uint32_t parity = 0;
+    const uint32_t r1_row = buf + j * 128;
+    const uint32_t r1_xor = (j & 7) << 4;
+    const uint32_t r2_col = buf + (j >> 5) * (kF_PolyBytes / 2) + (j & 3) * 4;
+    const uint32_t r2_chunk = ((j & 31) >> 2) << 4;
+
+    auto tile_index = [&](uint32_t i) -> uint32_t {   // T-item i of this class -> tile in memory
+        const uint32_t p = i / K, k = i - p * K;
+        return p * G + cta_half * 8 + 2 * k + parity_h;
+    };
+    if (tq < t_total && j == 0) {
+        const int tile = (int) tile_index(tq);
+        mbar_expect_tx(bar, kF_PolyBytes);
+        tma_load_3d(buf, &map_lo, bar, 0, 0, tile);
+        tma_load_3d(buf + kF_PolyBytes / 2, &map_hi, bar, 0, 0, tile);
+    }
+    // A warp publishes its share of a finished tile: its lanes' stores, then one release
+    // increment (2 warps per tile -> a polynomial is complete at 2G).  Deferred to the middle
+    // of the team's next T-item, when those stores have long left the SM and the fence is cheap.
+    uint32_t pending = 0xffffffffu;
+    auto publish = [&]() {
+        if (pending != 0xffffffffu) {
+            __syncwarp();
+            if ((tid & 31) == 0) {
+                asm volatile("fence.acq_rel.gpu;" ::: "memory");
+                asm volatile("red.relaxed.gpu.global.add.u32 [%0], 1;" ::"l"(prm.done + pending) : "memory");
+            }
+            pending = 0xffffffffu;
+        }
+    };
+    // The counter of the team's next C-item is read early (every thread for itself, one
+    // broadcast transaction per warp), so the check at the start of the item costs nothing
+    // when the polynomial is complete -- which the lag makes the normal case.
+    uint32_t ctr_val = 0;
+    auto prefetch_counter = [&]() {
+        if (cq < c_total) ctr_val = ld_counter(prm.done + cq / G);
+    };
+    prefetch_counter();
+
+    while (tq < t_total || cq < c_total) {
+        // ---- C-items whose polynomial trails this team's next T-item by at least `lag`
+        // (lag > one queue step, so the wait targets a polynomial below every unpublished
+        // tile of the slowest team: no cycle), or any C-item once the T-items are exhausted
+        // (then nothing of this team is pending while it waits)
+        const bool t_left = tq < t_total;
+        const uint32_t t_poly = t_left ? tq / K : 0;
+        while (cq < c_total && (!t_left || cq / G + prm.lag <= t_poly)) {
+            const uint32_t p = cq / G, k = cq - p * G;
+            if (!t_left) publish();
+            if (ctr_val < 2 * G) {
+                uint32_t spins = 0;
+                while ((ctr_val = ld_counter(prm.done + p)) < 2 * G) {
+                    __nanosleep(64);
+                    if (++spins > kTC_SpinLimit) {
+                        atomicExch(prm.error, 1u);
+                        break;
+                    }
+                }
+            }
+            uint32_t *base = prm.out + ((size_t) p << (12 + LOGG)) + k * (4096 / G) + 4 * j;
+            uint32_t w[64];
+#pragma unroll
+            for (int tt = 0; tt < G; tt++) {
+#pragma unroll
+                for (int u = 0; u < U; u++) {
+                    const uint4 x = ldcg128(base + tt * 4096 + u * 256);
+                    w[(tt * U + u) * 4 + 0] = x.x;
+                    w[(tt * U + u) * 4 + 1] = x.y;
+                    w[(tt * U + u) * 4 + 2] = x.z;
+                    w[(tt * U + u) * 4 + 3] = x.w;
+                }
+            }
+            cq += num_teams;
+            prefetch_counter();
+            // stages 12 .. 12+LOGG-1 pair tiles tt and tt + 2^m, twiddle table[(G >> (m+1)) + block]
+#pragma unroll
+            for (int m = 0; m < LOGG; m++) {
+#pragma unroll
+                for (int b2 = 0; b2 < (G >> (m + 1)); b2++) {
+                    const uint32_t cw = cross.w[(G >> (m + 1)) + b2], cwp = cross.wp[(G >> (m + 1)) + b2];
+#pragma unroll
+                    for (int e = 0; e < (1 << m); e++) {
+                        const int t0 = (b2 << (m + 1)) + e;
+#pragma unroll
+                        for (int x = 0; x < U * 4; x++) {
+                            if (m == 0) {
+                                gs_bfly<false>(w[t0 * U * 4 + x], w[(t0 + 1) * U * 4 + x], cw, cwp, q, two_q,
+                                               zero);
+                            } else {
+                                gs_bfly<true>(w[t0 * U * 4 + x], w[(t0 + (1 << m)) * U * 4 + x], cw, cwp, q,
+                                              two_q, zero);
+                            }
+                        }
+                    }
+                }
+            }
+#pragma unroll
+            for (int tt = 0; tt < G; tt++) {
+#pragma unroll
+                for (int u = 0; u < U; u++) {
+                    uint32_t o[4];
+#pragma unroll
+                    for (int e = 0; e < 4; e++) {
+                        uint32_t r = w[(tt * U + u) * 4 + e];
+                        if (DUAL) r = shoup_mul_lazy(r, prm.scale, prm.scale_shoup, q);
+                        o[e] = min(r - q, r);   // every butterfly output is in [0, 2q)
+                    }
+                    *reinterpret_cast<uint4 *>(base + tt * 4096 + u * 256) = make_uint4(o[0], o[1], o[2], o[3]);
+                }
+            }
+        }
+        if (!t_left) continue;
+
+        // ---- T-item: stages 0..11 of one tile
+        const uint32_t p = tq / K, k = tq - p * K;
+        const uint32_t tile_cur = tile_index(tq);
+        const uint32_t tw1 = lane_base + k * 128u;
+        const Tw16c tw2{r2base + (2 * k + parity_h) * 512u};
+        uint32_t v[64];
+        mbar_wait(bar, parity);
+        parity ^= 1;
+#pragma unroll
+        for (int c = 0; c < 16; c++) {
+            uint4 x = lds128(r1_row + (c >> 3) * (kF_PolyBytes / 2) + (((c & 7) << 4) ^ r1_xor));
+            v[4 * c + 0] = x.x;
+            v[4 * c + 1] = x.y;
+            v[4 * c + 2] = x.z;
+            v[4 * c + 3] = x.w;
+        }
+        if (DUAL) {
+            // second operand through the same buffer, then v = a*b*2^-32 mod q in (0, 2q)
+            fence_proxy_async();
+            team_sync(team);
+            if (j == 0) {
+                mbar_expect_tx(bar, kF_PolyBytes);
+                tma_load_3d(buf, &map_b_lo, bar, 0, 0, (int) tile_cur);
+                tma_load_3d(buf + kF_PolyBytes / 2, &map_b_hi, bar, 0, 0, (int) tile_cur);
+            }
+            mbar_wait(bar, parity);
+            parity ^= 1;
+#pragma unroll
+            for (int c = 0; c < 16; c++) {
+                uint4 x = lds128(r1_row + (c >> 3) * (kF_PolyBytes / 2) + (((c & 7) << 4) ^ r1_xor));
+                const uint32_t bb[4] = {x.x, x.y, x.z, x.w};
+#pragma unroll
+                for (int e = 0; e < 4; e++) {
+                    uint64_t prod = (uint64_t) v[4 * c + e] * bb[e];
+                    uint32_t m = (uint32_t) prod * prm.qinv;
+                    v[4 * c + e] = (uint32_t) (prod >> 32) - __umulhi(m, q) + q;
+                }
+            }
+        }
+        gs_round_tmem<DUAL>(v, tw1, q, two_q, zero);
+#pragma unroll
+        for (int c = 0; c < 16; c++) {
+            sts128(r1_row + (c >> 3) * (kF_PolyBytes / 2) + (((c & 7) << 4) ^ r1_xor), v[4 * c],
+                   v[4 * c + 1], v[4 * c + 2], v[4 * c + 3]);
+        }
+        team_sync(team);
+#pragma unroll
+        for (int i = 0; i < 64; i++) {
+            v[i] = lds32(r2_col + i * 128 + (r2_chunk ^ ((i & 7) << 4)));
+        }
+        fence_proxy_async();
+        team_sync(team);
+        // ---- the buffer is free: prefetch this team's next tile; publish the previous one
+        tq += class_teams;
+        if (tq < t_total && j == 0) {
+            const int tile = (int) tile_index(tq);
+            mbar_expect_tx(bar, kF_PolyBytes);
+            tma_load_3d(buf, &map_lo, bar, 0, 0, tile);
+            tma_load_3d(buf + kF_PolyBytes / 2, &map_hi, bar, 0, 0, tile);
+        }
+        publish();
+        if (ctr_val < 2 * G) prefetch_counter();   // the next C-item's polynomial was incomplete
+        gs_round<true>(v, tw2, q, two_q, zero);
+        uint32_t *dst = prm.out + (size_t) tile_cur * 4096 + j;
+#pragma unroll
+        for (int i = 0; i < 64; i++) {
+            dst[i * 64] = min(v[i] - q, v[i]);
+        }
+        pending = p;
+    }
+    publish();
+    tmem_fence_before_sync();
+    __syncthreads();
+    if (warp == 0) tmem_dealloc_512(tmem_base);
+}
+
+// --------------------------------------------------------------------- host side
+int tile_maps(CUtensorMap *lo, CUtensorMap *hi, const int32_t *base, size_t tiles);  // kernels_fused.cu
+
+int tilecol_prepare() {
+    const auto attr = cudaFuncAttributeMaxDynamicSharedMemorySize;
+    NTTB200_CUDA(cudaFuncSetAttribute(tilecol_gs_kernel<1, false>, attr, kTC_SmemBytes));
+    NTTB200_CUDA(cudaFuncSetAttribute(tilecol_gs_kernel<2, false>, attr, kTC_SmemBytes));
+    NTTB200_CUDA(cudaFuncSetAttribute(tilecol_gs_kernel<3, false>, attr, kTC_SmemBytes));
+    NTTB200_CUDA(cudaFuncSetAttribute(tilecol_gs_kernel<4, false>, attr, kTC_SmemBytes));
+    NTTB200_CUDA(cudaFuncSetAttribute(tilecol_gs_kernel<1, true>, attr, kTC_SmemBytes));
+    NTTB200_CUDA(cudaFuncSetAttribute(tilecol_gs_kernel<2, true>, attr, kTC_SmemBytes));
+    NTTB200_CUDA(cudaFuncSetAttribute(tilecol_gs_kernel<3, true>, attr, kTC_SmemBytes));
+    NTTB200_CUDA(cudaFuncSetAttribute(tilecol_gs_kernel<4, true>, attr, kTC_SmemBytes));
+    return NTTB200_OK;
+}
+
+static uint32_t tc_inv_mod_2_32(uint32_t q) {  // q odd
+    uint32_t x = q;
+    for (int i = 0; i < 5; i++) x *= 2u - q * x;
+    return x;
+}
+
+// which transform lengths take this kernel: 16 by default -- measured at 2^28 coefficients:
+// 0.439 of the HBM roofline against 0.403 for the two passes; for N = 2^13..2^15 the
+// one-CTA-per-polynomial kernels of kernels_poly.cu are faster (0.50/0.49/0.42 against
+// 0.42/0.41/0.38).  NTTB200_TILECOL_LOGN="13,14,15,16" overrides (empty string = none).
+static bool tilecol_enabled(uint32_t logn) {
+    static const uint32_t mask = []() {
+        const char *e = getenv("NTTB200_TILECOL_LOGN");
+        if (!e) return 1u << 16;
+        uint32_t m = 0;
+        for (const char *c = e; *c;) {
+            int v = atoi(c);
+            if (v >= 13 && v <= 16) m |= 1u << v;
+            while (*c && *c != ',') c++;
+            if (*c == ',') c++;
+        }
+        return m;
+    }();
+    return (mask >> logn) & 1u;
+}
+
+template <int LOGG, bool DUAL>
+static void tilecol_gs_launch(int grid, cudaStream_t st, const CUtensorMap &a_lo, const CUtensorMap &a_hi,
+                              const CUtensorMap &b_lo, const CUtensorMap &b_hi, const TileColParams &tp,
+                              const CrossTw &cross) {
+    tilecol_gs_kernel<LOGG, DUAL><<<grid, kM_Threads, kTC_SmemBytes, st>>>(a_lo, a_hi, b_lo, b_hi, tp,
+                                                                          cross);
+}
+
+int launch_tilecol_gs(nttb200_plan *p, const int32_t *d_in, const int32_t *d_b, int32_t *d_out,
+                      size_t batch, cudaStream_t st) {
+    const int logg = (int) p->logn - 12;
+    if (logg < 1 || logg > 4 || !p->d_tw_tile || !tilecol_enabled(p->logn)) return NTTB200_ERR_UNSUPPORTED;
+    const uint64_t tiles = (uint64_t) batch << logg;
+    if (tiles > 0x7fffffffull || ((uintptr_t) d_out & 15u)) return NTTB200_ERR_UNSUPPORTED;
+    CUtensorMap a_lo, a_hi, b_lo, b_hi;
+    if (tile_maps(&a_lo, &a_hi, d_in, (size_t) tiles) != NTTB200_OK) return NTTB200_ERR_UNSUPPORTED;
+    TileColParams tp;
+    tp.out = reinterpret_cast<uint32_t *>(d_out);
+    tp.tw_tile = p->d_tw_tile;
+    tp.batch = (uint32_t) batch;
+    tp.q = p->q;
+    tp.zero = 0;
+    tp.qinv = tp.scale = tp.scale_shoup = 0;
+    if (d_b) {
+        if (tile_maps(&b_lo, &b_hi, d_b, (size_t) tiles) != NTTB200_OK) return NTTB200_ERR_UNSUPPORTED;
+        tp.qinv = tc_inv_mod_2_32(p->q);
+        const uint64_t sc = ((uint64_t) p->n_inv << 32) % p->q;
+        tp.scale = (uint32_t) sc;
+        tp.scale_shoup = (uint32_t) ((sc << 32) / p->q);
+    } else {
+        b_lo = a_lo;
+        b_hi = a_hi;
+    }
+    // one CTA per SM, all co-resident; an even grid when the positions are split over two
+    // CTA classes (N = 2^16)
+    uint64_t ctas = (tiles + kM_Teams - 1) / kM_Teams;
+    int grid = (int) (ctas < (uint64_t) p->sm_count ? ctas : (uint64_t) p->sm_count);
+    if (logg == 4) grid = grid < 2 ? 2 : (grid & ~1);
+    static const long lag_pct = []() {
+        const char *e = getenv("NTTB200_TILECOL_LAG_PCT");
+        return e ? atol(e) : 150L;
+    }();
+    // in flight at any time: one tile per team; trail by lag_pct % of that, in polynomials
+    const uint64_t lag_tiles = (uint64_t) grid * kM_Teams * (uint64_t) (lag_pct < 100 ? 100 : lag_pct) / 100;
+    tp.lag = (uint32_t) ((lag_tiles >> logg) + 2);   // > one queue step (grid * 8 / G polynomials)
+    // counters: one per polynomial + the error word, stream-ordered scratch
+    uint32_t *ctr = nullptr;
+    NTTB200_CUDA(cudaMallocAsync(&ctr, sizeof(uint32_t) * (batch + 1), st));
+    NTTB200_CUDA(cudaMemsetAsync(ctr, 0, sizeof(uint32_t) * (batch + 1), st));
+    tp.done = ctr;
+    tp.error = ctr + batch;
+    const bool dual = d_b != nullptr;
+    switch (logg * 2 + (dual ? 1 : 0)) {
+        case 2: tilecol_gs_launch<1, false>(grid, st, a_lo, a_hi, b_lo, b_hi, tp, p->cross_tw); break;
+        case 3: tilecol_gs_launch<1, true>(grid, st, a_lo, a_hi, b_lo, b_hi, tp, p->cross_tw); break;
+        case 4: tilecol_gs_launch<2, false>(grid, st, a_lo, a_hi, b_lo, b_hi, tp, p->cross_tw); break;
+        case 5: tilecol_gs_launch<2, true>(grid, st, a_lo, a_hi, b_lo, b_hi, tp, p->cross_tw); break;
+        case 6: tilecol_gs_launch<3, false>(grid, st, a_lo, a_hi, b_lo, b_hi, tp, p->cross_tw); break;
+        case 7: tilecol_gs_launch<3, true>(grid, st, a_lo, a_hi, b_lo, b_hi, tp, p->cross_tw); break;
+        case 8: tilecol_gs_launch<4, false>(grid, st, a_lo, a_hi, b_lo, b_hi, tp, p->cross_tw); break;
+        default: tilecol_gs_launch<4, true>(grid, st, a_lo, a_hi, b_lo, b_hi, tp, p->cross_tw); break;
+    }
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+    cudaError_t e = cudaGetLastError();
+    cudaError_t e2 = cudaFreeAsync(ctr, st);
+    if (e != cudaSuccess) return cuda_fail(e, "tilecol_gs_kernel");
+    if (e2 != cudaSuccess) return cuda_fail(e2, "cudaFreeAsync");
+    p->last_path = dual ? "tilecol_persistent_dual" : "tilecol_persistent";
+    return NTTB200_OK;
+}
+
+}  // namespace nttb200
