@@ -43,8 +43,11 @@ extern "C" {
 typedef enum nttb200_status {
     NTTB200_OK = 0,
     NTTB200_ERR_INVALID_ARG = 1, /* null pointer, logn out of range, bad flags      */
-    NTTB200_ERR_MODULUS = 2,     /* q outside [2, 2^30] (the golden's own domain:   */
-                                 /* 2q-1 <= INT32_MAX, src/test.cpp:48,50)          */
+    NTTB200_ERR_MODULUS = 2,     /* q outside [2, 2^31).  q <= 2^30 is the golden's  */
+                                 /* own domain (2q-1 <= INT32_MAX, src/test.cpp:     */
+                                 /* 48,50) and takes the fast kernels; 2^30 < q <    */
+                                 /* 2^31 is served by the canonical stage-pass       */
+                                 /* kernels (wider moduli, outside the reference)    */
     NTTB200_ERR_TABLE = 3,       /* table entry outside [0, q)                      */
     NTTB200_ERR_CUDA = 4,        /* a CUDA call failed; see nttb200_last_error()    */
     NTTB200_ERR_NO_DEVICE = 5,   /* no CUDA device / wrong device ordinal           */
@@ -63,6 +66,13 @@ typedef enum nttb200_status {
                                     /* (src/test.cpp:46-50; e.g. a[i] = i with n > p); costs one     */
                                     /* extra pass.  Without it device inputs must be in [0, q).      */
                                     /* nttb200_gs_host always reduces (the pass hides behind PCIe).  */
+
+#define NTTB200_INPUT_BITREV 8u     /* layout adapters (new): the input is stored in    */
+#define NTTB200_OUTPUT_BITREV 16u   /* bit-reversed order / the output is delivered in bit-reversed  */
+                                    /* order (index i <-> bitrev_logn(i) inside every polynomial).   */
+                                    /* Fused into the load / store of the N = 4096 golden kernel     */
+                                    /* (no extra pass); one permutation pass elsewhere.  Not         */
+                                    /* combinable with NTTB200_ORDER_AIE_DEVICE.                     */
 
 #define NTTB200_MAX_LOGN 27
 
@@ -95,7 +105,7 @@ NTTB200_API int32_t nttb200_powmod(int32_t b, int64_t e, int32_t m);
 
 /* Replaces device image load + bo_root fill/sync (src/test.cpp:110-112,137-151).
  * table_host: N = 2^logn int32 words on the host, index rule above.  1 <= logn <=
- * NTTB200_MAX_LOGN, 2 <= q <= 2^30. */
+ * NTTB200_MAX_LOGN, 2 <= q < 2^31 (see NTTB200_ERR_MODULUS). */
 NTTB200_API int nttb200_plan_create(nttb200_plan **plan, int device, uint32_t logn, uint32_t q,
                                     const int32_t *table_host, uint32_t flags);
 NTTB200_API int nttb200_plan_destroy(nttb200_plan *plan);
@@ -176,6 +186,11 @@ NTTB200_API int nttb200_gs_host(nttb200_plan *plan, const int32_t *h_in, int32_t
  * `.map<int32_t*>()` (src/test.cpp:115-134).  write_combined != 0 asks for
  * write-combined memory (fast for the device to read, slow for the CPU to read back:
  * use it for inputs only). */
+/* out[b][i] = in[b][bitrev_logn(i)] for batch polynomials (in place allowed): the
+ * standalone bit-reversal adapter. */
+NTTB200_API int nttb200_bitrev_permute(nttb200_plan *plan, const int32_t *d_in, int32_t *d_out,
+                                       size_t batch, void *cuda_stream);
+
 /* out[i] = in[i] mod q in [0, q) for ANY int32 words (device pointers): the reduction the
  * golden applies with `%` when it first touches an input (src/test.cpp:46-50). */
 NTTB200_API int nttb200_reduce(nttb200_plan *plan, const int32_t *d_in, int32_t *d_out,

@@ -19,6 +19,8 @@ from .api import (  # noqa: F401
     ORDER_GOLDEN,
     FORCE_GENERIC,
     REDUCE_INPUT,
+    INPUT_BITREV,
+    OUTPUT_BITREV,
     GEN_POWERS,
     GEN_BITREV,
     kernel_launches,

@@ -16,6 +16,8 @@ ORDER_GOLDEN = 0
 ORDER_AIE_DEVICE = 1
 FORCE_GENERIC = 2
 REDUCE_INPUT = 4
+INPUT_BITREV = 8
+OUTPUT_BITREV = 16
 GEN_POWERS = 0
 GEN_BITREV = 1
 
@@ -59,6 +61,7 @@ def load_library():
                                                          u32, u32, u32, u32]),
         "nttb200_plan_table": (ctypes.c_int, [vp, _i32p]),
         "nttb200_reduce": (ctypes.c_int, [vp, vp, vp, sz, vp]),
+        "nttb200_bitrev_permute": (ctypes.c_int, [vp, vp, vp, sz, vp]),
         "nttb200_gs_batch": (ctypes.c_int, [vp, vp, vp, sz, ctypes.c_int, vp]),
         "nttb200_ct_batch": (ctypes.c_int, [vp, vp, vp, sz, ctypes.c_int, vp]),
         "nttb200_gs_stage_range": (ctypes.c_int, [vp, vp, vp, sz, ctypes.c_int, ctypes.c_int, vp]),
@@ -96,6 +99,7 @@ def load_library():
 EXPORTED_SYMBOLS = (
     "nttb200_make_roots", "nttb200_make_bitrev_table", "nttb200_powmod", "nttb200_plan_create",
     "nttb200_plan_destroy", "nttb200_plan_create_generated", "nttb200_plan_table", "nttb200_reduce",
+    "nttb200_bitrev_permute",
     "nttb200_gs_batch", "nttb200_ct_batch", "nttb200_gs_stage_range",
     "nttb200_gs_host", "nttb200_gs_stage_range_scatter", "nttb200_host_alloc", "nttb200_host_free",
     "nttb200_pointwise", "nttb200_scale", "nttb200_polymul_negacyclic",
@@ -252,6 +256,11 @@ class Plan:
         out = np.empty(self.n, dtype=np.int32)
         _check(self._lib.nttb200_plan_table(self._h, out.ctypes.data_as(_i32p)), "plan_table")
         return out
+
+    def bitrev_permute(self, d_in, d_out, batch: int, stream=None) -> None:
+        """out[b][i] = in[b][bitrev(i)] (in place allowed)."""
+        _check(self._lib.nttb200_bitrev_permute(self._h, _addr(d_in), _addr(d_out), batch,
+                                                _stream(stream)), "bitrev_permute")
 
     def reduce(self, d_in, d_out, count: int, stream=None) -> None:
         """out = in mod q for arbitrary int32 words (the golden's `%` on first touch)."""

@@ -84,7 +84,7 @@ extern "C" {
 
 /* ---------------------------------------------------------------- tables */
 int nttb200_make_roots(int32_t n, int32_t *roots, int32_t p, int32_t g) {
-    if (!roots || n < 1 || p < 2 || p > (1 << 30) || g < 0) return NTTB200_ERR_INVALID_ARG;
+    if (!roots || n < 1 || p < 2 || g < 0) return NTTB200_ERR_INVALID_ARG;  // p < 2^31 by type
     // src/test.cpp:137-139 (roots[0] = 1) and :27-32 (w = g^((p-1)/n), running product)
     uint64_t w = powmod64((uint64_t) g, (uint64_t) ((p - 1) / n), (uint64_t) p);
     roots[0] = 1;
@@ -97,7 +97,7 @@ int nttb200_make_roots(int32_t n, int32_t *roots, int32_t p, int32_t g) {
 }
 
 int nttb200_make_bitrev_table(int32_t n, int32_t *table, int32_t p, int32_t base) {
-    if (!table || n < 1 || (n & (n - 1)) || p < 2 || p > (1 << 30) || base < 0) {
+    if (!table || n < 1 || (n & (n - 1)) || p < 2 || base < 0) {
         return NTTB200_ERR_INVALID_ARG;
     }
     int logn = 0;
@@ -127,11 +127,19 @@ static int plan_begin(nttb200_plan **out, int device, uint32_t logn, uint32_t q,
     if (!out) return NTTB200_ERR_INVALID_ARG;
     *out = nullptr;
     if (logn < 1 || logn > NTTB200_MAX_LOGN) return NTTB200_ERR_INVALID_ARG;
-    if (flags & ~(NTTB200_ORDER_AIE_DEVICE | NTTB200_FORCE_GENERIC | NTTB200_REDUCE_INPUT)) {
+    if (flags & ~(NTTB200_ORDER_AIE_DEVICE | NTTB200_FORCE_GENERIC | NTTB200_REDUCE_INPUT |
+                  NTTB200_INPUT_BITREV | NTTB200_OUTPUT_BITREV)) {
+        return NTTB200_ERR_INVALID_ARG;
+    }
+    if ((flags & NTTB200_ORDER_AIE_DEVICE) && (flags & (NTTB200_INPUT_BITREV | NTTB200_OUTPUT_BITREV))) {
         return NTTB200_ERR_INVALID_ARG;
     }
     if ((flags & NTTB200_ORDER_AIE_DEVICE) && logn < 4) return NTTB200_ERR_INVALID_ARG;
-    if (q < 2 || q > (1u << 30)) return NTTB200_ERR_MODULUS;
+    if (q < 2 || q > 0x7fffffffu) return NTTB200_ERR_MODULUS;
+    // 2^30 < q < 2^31 (outside the golden's int32 domain): the lazy [0,2q) /
+    // [0,4q) butterflies of the register-radix kernels need 4q <= 2^32, so these moduli run
+    // on the stage-pass kernels, whose intermediates are canonical (sums below 2q < 2^32)
+    if (q > (1u << 30)) flags |= NTTB200_FORCE_GENERIC;
     int count = 0;
     cudaError_t e = cudaGetDeviceCount(&count);
     if (e != cudaSuccess) return cuda_fail(e, "cudaGetDeviceCount");
@@ -204,7 +212,7 @@ int nttb200_plan_create(nttb200_plan **out, int device, uint32_t logn, uint32_t 
                         const int32_t *table_host, uint32_t flags) {
     if (out) *out = nullptr;
     if (!table_host || logn < 1 || logn > NTTB200_MAX_LOGN) return NTTB200_ERR_INVALID_ARG;
-    if (q >= 2 && q <= (1u << 30)) {
+    if (q >= 2 && q <= 0x7fffffffu) {
         const uint32_t n = 1u << logn;
         for (uint32_t i = 1; i < n; i++) {  // table[0] is never read (src/test.cpp:45: h >= 1)
             if (table_host[i] < 0 || (uint32_t) table_host[i] >= q) return NTTB200_ERR_TABLE;
@@ -283,6 +291,9 @@ int nttb200_plan_destroy(nttb200_plan *p) {
 }
 
 /* -------------------------------------------------------------- hot path */
+static int run_gs_core(nttb200_plan *p, const int32_t *d_in, int32_t *d_out, size_t batch,
+                       int stage_limit, cudaStream_t st);
+
 static int run_gs(nttb200_plan *p, const int32_t *d_in, int32_t *d_out, size_t batch,
                   int stage_limit, cudaStream_t st, bool reduce_first = false) {
     if (batch == 0) return NTTB200_OK;
@@ -292,6 +303,27 @@ static int run_gs(nttb200_plan *p, const int32_t *d_in, int32_t *d_out, size_t b
         if (rc != NTTB200_OK) return rc;
         d_in = d_out;
     }
+    const bool in_br = p->flags & NTTB200_INPUT_BITREV, out_br = p->flags & NTTB200_OUTPUT_BITREV;
+    if (in_br || out_br) {
+        // fused into the N = 4096 kernel's load / store; one permutation pass elsewhere
+        if (full_depth(p, stage_limit) && !(p->flags & NTTB200_FORCE_GENERIC)) {
+            int rc = launch_fused_gs_bitrev(p, d_in, d_out, batch, in_br, out_br, st);
+            if (rc != NTTB200_ERR_UNSUPPORTED) return rc;
+        }
+        if (in_br) {
+            int rc = launch_bitrev_permute(p, d_in, d_out, batch, st);
+            if (rc != NTTB200_OK) return rc;
+            d_in = d_out;
+        }
+        int rc = run_gs_core(p, d_in, d_out, batch, stage_limit, st);
+        if (rc == NTTB200_OK && out_br) rc = launch_bitrev_permute(p, d_out, d_out, batch, st);
+        return rc;
+    }
+    return run_gs_core(p, d_in, d_out, batch, stage_limit, st);
+}
+
+static int run_gs_core(nttb200_plan *p, const int32_t *d_in, int32_t *d_out, size_t batch,
+                       int stage_limit, cudaStream_t st) {
     const bool full = full_depth(p, stage_limit);
     const bool permute = full && (p->flags & NTTB200_ORDER_AIE_DEVICE);
     if (full && !(p->flags & NTTB200_FORCE_GENERIC)) {
@@ -326,6 +358,11 @@ int nttb200_gs_batch(nttb200_plan *p, const int32_t *d_in, int32_t *d_out, size_
     return run_gs(p, d_in, d_out, batch, stage_limit, (cudaStream_t) stream);
 }
 
+}  // extern "C"
+static int ct_core(nttb200_plan *p, const int32_t *d_in, int32_t *d_out, size_t batch, int stage_limit,
+                   void *stream);
+extern "C" {
+
 int nttb200_ct_batch(nttb200_plan *p, const int32_t *d_in, int32_t *d_out, size_t batch,
                      int stage_limit, void *stream) {
     if (!p || (batch && (!d_in || !d_out))) return NTTB200_ERR_INVALID_ARG;
@@ -336,6 +373,23 @@ int nttb200_ct_batch(nttb200_plan *p, const int32_t *d_in, int32_t *d_out, size_
         if (rc != NTTB200_OK) return rc;
         d_in = d_out;
     }
+    if (p->flags & NTTB200_INPUT_BITREV) {
+        int rc = launch_bitrev_permute(p, d_in, d_out, batch, (cudaStream_t) stream);
+        if (rc != NTTB200_OK) return rc;
+        d_in = d_out;
+    }
+    if (p->flags & NTTB200_OUTPUT_BITREV) {
+        int rc = ct_core(p, d_in, d_out, batch, stage_limit, (cudaStream_t) stream);
+        if (rc == NTTB200_OK) rc = launch_bitrev_permute(p, d_out, d_out, batch, (cudaStream_t) stream);
+        return rc;
+    }
+    return ct_core(p, d_in, d_out, batch, stage_limit, (cudaStream_t) stream);
+}
+
+}  // extern "C"
+
+static int ct_core(nttb200_plan *p, const int32_t *d_in, int32_t *d_out, size_t batch, int stage_limit,
+                   void *stream) {
     // CT stage idx (0 = stride N/2) acts on index bit logn-1-idx
     const bool full = full_depth(p, stage_limit);
     int sb = full ? 0 : (int) p->logn - 1 - stage_limit;
@@ -357,6 +411,15 @@ int nttb200_ct_batch(nttb200_plan *p, const int32_t *d_in, int32_t *d_out, size_
     p->last_path = "generic_stage_pass";
     return launch_generic(p, d_in, d_out, batch, sb, (int) p->logn, /*ct=*/true, false,
                           (cudaStream_t) stream);
+}
+
+extern "C" {
+
+int nttb200_bitrev_permute(nttb200_plan *p, const int32_t *d_in, int32_t *d_out, size_t batch,
+                           void *stream) {
+    if (!p || (batch && (!d_in || !d_out))) return NTTB200_ERR_INVALID_ARG;
+    DeviceGuard guard(p->device);
+    return launch_bitrev_permute(p, d_in, d_out, batch, (cudaStream_t) stream);
 }
 
 int nttb200_gs_stage_range(nttb200_plan *p, const int32_t *d_in, int32_t *d_out, size_t batch,
@@ -696,7 +759,7 @@ const char *nttb200_strerror(int status) {
     switch (status) {
         case NTTB200_OK: return "ok";
         case NTTB200_ERR_INVALID_ARG: return "invalid argument";
-        case NTTB200_ERR_MODULUS: return "modulus outside [2, 2^30] (or even where N^-1 is needed)";
+        case NTTB200_ERR_MODULUS: return "modulus outside [2, 2^31) (or even where N^-1 is needed)";
         case NTTB200_ERR_TABLE: return "twiddle table entry outside [0, q)";
         case NTTB200_ERR_CUDA: return "CUDA error (see nttb200_last_error)";
         case NTTB200_ERR_NO_DEVICE: return "no usable CUDA device; this library has no CPU path";

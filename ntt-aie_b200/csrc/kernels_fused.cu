@@ -45,6 +45,11 @@ constexpr int kF_TwSlots = 32;            // uint4 slots of round-1 twiddles per
 constexpr int kF_TwBytes = kF_TwSlots * kF_Team * 16;   // 32 KiB
 constexpr int kF_SmemBytes = kF_TwBytes + kF_Teams * kF_PolyBytes + 64 + 1024;
 
+__host__ __device__ constexpr int kBitrev6(int x) {
+    return ((x & 1) << 5) | ((x & 2) << 3) | ((x & 4) << 1) | ((x & 8) >> 1) | ((x & 16) >> 3) |
+           ((x & 32) >> 5);
+}
+
 // last stage: canonical outputs in [0, q)
 __device__ __forceinline__ void gs_bfly_final(uint32_t &x, uint32_t &y, uint32_t w, uint32_t wp,
                                               uint32_t q, uint32_t two_q, uint32_t zero) {
@@ -115,9 +120,17 @@ struct FusedParams {
     uint32_t scale_shoup; // N^-1 of an inverse transform, fused into the store
 };
 
-// TWTMEM: the round-1 private twiddles live in tensor memory (128 columns, lanes = threads)
-// instead of the 32 KiB shared-memory table.
-template <bool PERMUTE, bool SCALE = false, bool LOCKSTEP = false, bool TWTMEM = false>
+// IN_BR / OUT_BR: layout adapters fused into the load and the store: the input
+// is stored in bit-reversed order / the output is wanted in bit-reversed order.  Index
+// n = 64 r + c maps to bitrev12(n) = 64 bitrev6(c) + bitrev6(r), so "row j of the natural
+// polynomial" is column bitrev6(j) of the stored tile, rows taken in bit-reversed order --
+// a column read with compile-time register renaming; and the natural coefficient j + 64 i
+// lands in row bitrev6(j), column bitrev6(i) -- thread j writes one 256 B row from
+// compile-time-permuted registers.  No extra pass over HBM in either case.
+// (Measured and kept out of this kernel: round-1 twiddles in tensor memory instead of the
+// 32 KiB shared-memory table, 0.471 against 0.462 ms; CTA-wide instead of team barriers,
+// 0.516 ms.)
+template <bool PERMUTE, bool SCALE = false, bool IN_BR = false, bool OUT_BR = false>
 __global__ void __launch_bounds__(kF_Threads, 1)
 fused_gs4096_kernel(const __grid_constant__ CUtensorMap map_lo,
                     const __grid_constant__ CUtensorMap map_hi,
@@ -138,42 +151,13 @@ fused_gs4096_kernel(const __grid_constant__ CUtensorMap map_lo,
     const uint32_t q = prm.q, two_q = 2u * prm.q, zero = prm.zero;
 
     // stage the round-1 twiddles (kernel-private order, prepared at plan time)
-    uint32_t tmem_base = 0, tw_taddr = 0;
-    if (TWTMEM) {
-        const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);
-        if (warp == 0) tmem_alloc_512(bar_base + 64);
-        tmem_fence_before_sync();
-        __syncthreads();
-        tmem_fence_after_sync();
-        tmem_base = lds32(bar_base + 64);
-        tw_taddr = tmem_base + ((uint32_t) (warp & 3) << 21);
-        if (warp < 4) {  // teams 0 and 1 cover all 128 lanes
-#pragma unroll 1
-            for (int g = 0; g < 8; g++) {
-                uint32_t r[16];
-#pragma unroll
-                for (int k = 0; k < 4; k++) {
-                    const uint4 x = __ldg(prm.tw_r1 + (size_t) (4 * g + k) * kF_Team + j);
-                    r[4 * k + 0] = x.x;
-                    r[4 * k + 1] = x.y;
-                    r[4 * k + 2] = x.z;
-                    r[4 * k + 3] = x.w;
-                }
-                tmem_st16(tw_taddr + 16u * g, r);
-            }
-            tmem_wait_st();
-        }
-        tmem_fence_before_sync();
-    } else {
-        for (int i = tid; i < kF_TwSlots * kF_Team; i += kF_Threads) {
-            uint4 t = __ldg(prm.tw_r1 + i);
-            sts128(tw_base + i * 16, t.x, t.y, t.z, t.w);
-        }
+    for (int i = tid; i < kF_TwSlots * kF_Team; i += kF_Threads) {
+        uint4 t = __ldg(prm.tw_r1 + i);
+        sts128(tw_base + i * 16, t.x, t.y, t.z, t.w);
     }
     if (tid < kF_Teams) mbar_init(bar_base + tid * 8, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     __syncthreads();
-    if (TWTMEM) tmem_fence_after_sync();
 
     const uint32_t buf = data_base + team * kF_PolyBytes;
     const uint32_t bar = bar_base + team * 8;
@@ -195,6 +179,9 @@ fused_gs4096_kernel(const __grid_constant__ CUtensorMap map_lo,
     const uint32_t r2_col = buf + (j >> 5) * (kF_PolyBytes / 2) + (j & 3) * 4;  // round 2: column j
     const uint32_t r2_chunk = ((j & 31) >> 2) << 4;
     const uint32_t tw_addr = tw_base + j * 16;
+    const uint32_t jr = __brev((uint32_t) j) >> 26;   // bitrev6(j)
+    const uint32_t br_col = buf + (jr >> 5) * (kF_PolyBytes / 2) + (jr & 3) * 4;
+    const uint32_t br_chunk = ((jr & 31) >> 2) << 4;
 
     for (; poly < prm.batch; poly += stride) {
         uint32_t v[64];
@@ -202,24 +189,29 @@ fused_gs4096_kernel(const __grid_constant__ CUtensorMap map_lo,
         parity ^= 1;
 
         // ---- round 1: rows -> registers, stages 0..5
+        if (IN_BR) {
+            // natural a[64j + c] = stored[64 bitrev6(c) + bitrev6(j)]: column bitrev6(j)
 #pragma unroll
-        for (int c = 0; c < 16; c++) {
-            uint4 t = lds128(r1_row + (c >> 3) * (kF_PolyBytes / 2) + (((c & 7) << 4) ^ r1_xor));
-            v[4 * c + 0] = t.x;
-            v[4 * c + 1] = t.y;
-            v[4 * c + 2] = t.z;
-            v[4 * c + 3] = t.w;
-        }
-        if (TWTMEM) {
-            gs_round_tmem<false>(v, tw_taddr, q, two_q, zero);
+            for (int r = 0; r < 64; r++) {
+                v[kBitrev6(r)] = lds32(br_col + r * 128 + (br_chunk ^ ((r & 7) << 4)));
+            }
+            team_sync(team);  // the row write below overwrites other threads' columns
         } else {
-            round1_stage<0>(v, tw_addr, q, two_q, zero);
-            round1_stage<1>(v, tw_addr, q, two_q, zero);
-            round1_stage<2>(v, tw_addr, q, two_q, zero);
-            round1_stage<3>(v, tw_addr, q, two_q, zero);
-            round1_stage<4>(v, tw_addr, q, two_q, zero);
-            round1_stage<5>(v, tw_addr, q, two_q, zero);
+#pragma unroll
+            for (int c = 0; c < 16; c++) {
+                uint4 t = lds128(r1_row + (c >> 3) * (kF_PolyBytes / 2) + (((c & 7) << 4) ^ r1_xor));
+                v[4 * c + 0] = t.x;
+                v[4 * c + 1] = t.y;
+                v[4 * c + 2] = t.z;
+                v[4 * c + 3] = t.w;
+            }
         }
+        round1_stage<0>(v, tw_addr, q, two_q, zero);
+        round1_stage<1>(v, tw_addr, q, two_q, zero);
+        round1_stage<2>(v, tw_addr, q, two_q, zero);
+        round1_stage<3>(v, tw_addr, q, two_q, zero);
+        round1_stage<4>(v, tw_addr, q, two_q, zero);
+        round1_stage<5>(v, tw_addr, q, two_q, zero);
 
         // ---- exchange through the same buffer (row write, column read)
 #pragma unroll
@@ -227,13 +219,13 @@ fused_gs4096_kernel(const __grid_constant__ CUtensorMap map_lo,
             sts128(r1_row + (c >> 3) * (kF_PolyBytes / 2) + (((c & 7) << 4) ^ r1_xor), v[4 * c],
                    v[4 * c + 1], v[4 * c + 2], v[4 * c + 3]);
         }
-        if (LOCKSTEP) __syncthreads(); else team_sync(team);
+        team_sync(team);
 #pragma unroll
         for (int i = 0; i < 64; i++) {
             v[i] = lds32(r2_col + i * 128 + (r2_chunk ^ ((i & 7) << 4)));
         }
         fence_proxy_async();
-        if (LOCKSTEP) __syncthreads(); else team_sync(team);
+        team_sync(team);
 
         // ---- the buffer is free: prefetch this team's next polynomial
         const uint64_t next = poly + stride;
@@ -252,6 +244,16 @@ fused_gs4096_kernel(const __grid_constant__ CUtensorMap map_lo,
         round2_stage<5>(v, uni, q, two_q, zero);
 
         // ---- store: register i is coefficient j + 64 i; a warp writes 128 B rows
+        if (OUT_BR) {
+            // coefficient j + 64 i goes to 64 bitrev6(j) + bitrev6(i): one 256 B row per thread
+            uint4 *row = reinterpret_cast<uint4 *>(prm.out + poly * kF_N + jr * 64);
+#pragma unroll
+            for (int a4 = 0; a4 < 16; a4++) {
+                row[a4] = make_uint4(v[kBitrev6(4 * a4)], v[kBitrev6(4 * a4 + 1)],
+                                     v[kBitrev6(4 * a4 + 2)], v[kBitrev6(4 * a4 + 3)]);
+            }
+            continue;
+        }
         uint32_t *dst = prm.out + poly * kF_N + j;
 #pragma unroll
         for (int i = 0; i < 64; i++) {
@@ -268,11 +270,6 @@ fused_gs4096_kernel(const __grid_constant__ CUtensorMap map_lo,
                 dst[row * 64] = v[i];
             }
         }
-    }
-    if (TWTMEM) {
-        tmem_fence_before_sync();
-        __syncthreads();
-        if (tid < 32) tmem_dealloc_512(tmem_base);
     }
 }
 
@@ -354,9 +351,11 @@ int fused_prepare(nttb200_plan *p) {
                                       cudaFuncAttributeMaxDynamicSharedMemorySize, kF_SmemBytes));
     NTTB200_CUDA(cudaFuncSetAttribute(fused_gs4096_kernel<false, true>,
                                       cudaFuncAttributeMaxDynamicSharedMemorySize, kF_SmemBytes));
-    NTTB200_CUDA(cudaFuncSetAttribute(fused_gs4096_kernel<false, false, true>,
+    NTTB200_CUDA(cudaFuncSetAttribute(fused_gs4096_kernel<false, false, true, false>,
                                       cudaFuncAttributeMaxDynamicSharedMemorySize, kF_SmemBytes));
     NTTB200_CUDA(cudaFuncSetAttribute(fused_gs4096_kernel<false, false, false, true>,
+                                      cudaFuncAttributeMaxDynamicSharedMemorySize, kF_SmemBytes));
+    NTTB200_CUDA(cudaFuncSetAttribute(fused_gs4096_kernel<false, false, true, true>,
                                       cudaFuncAttributeMaxDynamicSharedMemorySize, kF_SmemBytes));
     return NTTB200_OK;
 }
@@ -367,11 +366,19 @@ void fused_release(nttb200_plan *p) {
 }
 
 static int launch_fused_impl(nttb200_plan *p, const int32_t *d_in, int32_t *d_out, size_t batch,
-                             bool permute_out, bool scaled, cudaStream_t st);
+                             bool permute_out, bool scaled, cudaStream_t st, bool in_br = false,
+                             bool out_br = false);
 
 int launch_fused_gs(nttb200_plan *p, const int32_t *d_in, int32_t *d_out, size_t batch,
                     bool permute_out, cudaStream_t st) {
     return launch_fused_impl(p, d_in, d_out, batch, permute_out, false, st);
+}
+
+// golden network with the bit-reversal adapters fused into the load and/or the store
+int launch_fused_gs_bitrev(nttb200_plan *p, const int32_t *d_in, int32_t *d_out, size_t batch,
+                           bool in_br, bool out_br, cudaStream_t st) {
+    if (out_br && ((uintptr_t) d_out & 15u)) return NTTB200_ERR_UNSUPPORTED;
+    return launch_fused_impl(p, d_in, d_out, batch, false, false, st, in_br, out_br);
 }
 
 // golden network followed by a multiplication of every output by N^-1 * 2^32 mod q: the
@@ -383,7 +390,7 @@ int launch_fused_gs_scaled(nttb200_plan *p, const int32_t *d_in, int32_t *d_out,
 }
 
 static int launch_fused_impl(nttb200_plan *p, const int32_t *d_in, int32_t *d_out, size_t batch,
-                             bool permute_out, bool scaled, cudaStream_t st) {
+                             bool permute_out, bool scaled, cudaStream_t st, bool in_br, bool out_br) {
     if (p->logn != 12 || !p->d_tw_r1) return NTTB200_ERR_UNSUPPORTED;
     if (batch == 0) return NTTB200_OK;
     if (batch > 0x7fffffffull || ((uintptr_t) d_in & 15u) || ((uintptr_t) d_out & 3u)) {
@@ -414,11 +421,14 @@ static int launch_fused_impl(nttb200_plan *p, const int32_t *d_in, int32_t *d_ou
     } else if (permute_out) {
         fused_gs4096_kernel<true><<<grid, kF_Threads, kF_SmemBytes, st>>>(map_lo, map_hi, p->uni_gs,
                                                                           prm);
-    } else if (getenv("NTTB200_FUSED_TMEM")) {
-        fused_gs4096_kernel<false, false, false, true><<<grid, kF_Threads, kF_SmemBytes, st>>>(
+    } else if (in_br && out_br) {
+        fused_gs4096_kernel<false, false, true, true><<<grid, kF_Threads, kF_SmemBytes, st>>>(
             map_lo, map_hi, p->uni_gs, prm);
-    } else if (getenv("NTTB200_FUSED_LOCKSTEP") && batch % kF_Teams == 0) {
-        fused_gs4096_kernel<false, false, true><<<grid, kF_Threads, kF_SmemBytes, st>>>(
+    } else if (in_br) {
+        fused_gs4096_kernel<false, false, true, false><<<grid, kF_Threads, kF_SmemBytes, st>>>(
+            map_lo, map_hi, p->uni_gs, prm);
+    } else if (out_br) {
+        fused_gs4096_kernel<false, false, false, true><<<grid, kF_Threads, kF_SmemBytes, st>>>(
             map_lo, map_hi, p->uni_gs, prm);
     } else {
         fused_gs4096_kernel<false><<<grid, kF_Threads, kF_SmemBytes, st>>>(map_lo, map_hi,
@@ -426,7 +436,8 @@ static int launch_fused_impl(nttb200_plan *p, const int32_t *d_in, int32_t *d_ou
     }
     g_launches.fetch_add(1, std::memory_order_relaxed);
     NTTB200_CUDA(cudaGetLastError());
-    p->last_path = scaled ? "fused_gs4096_tma_scaled" : "fused_gs4096_tma";
+    p->last_path = scaled ? "fused_gs4096_tma_scaled"
+                          : (in_br || out_br) ? "fused_gs4096_tma_bitrev" : "fused_gs4096_tma";
     return NTTB200_OK;
 }
 

@@ -85,6 +85,8 @@ int build_shoup_table(nttb200_plan *p, const int32_t *d_table);
 int build_generated_table(nttb200_plan *p, uint32_t kind, uint32_t base, uint32_t gen_logn,
                           uint32_t block_mult);
 int build_tile_table(nttb200_plan *p);
+int launch_bitrev_permute(nttb200_plan *p, const int32_t *in, int32_t *out, size_t batch,
+                          cudaStream_t st);
 int launch_reduce(nttb200_plan *p, const int32_t *in, int32_t *out, size_t count, cudaStream_t st);
 
 // N = 2^13..2^15 in one pass, private twiddles in tensor memory (kernels_poly.cu)
@@ -120,6 +122,8 @@ int launch_scale(nttb200_plan *p, const int32_t *a, int32_t *c, size_t count, ui
 // back to the generic passes (still CUDA -- never a CPU path).
 int fused_prepare(nttb200_plan *p);
 void fused_release(nttb200_plan *p);
+int launch_fused_gs_bitrev(nttb200_plan *p, const int32_t *d_in, int32_t *d_out, size_t batch,
+                           bool in_br, bool out_br, cudaStream_t st);
 int launch_fused_gs(nttb200_plan *p, const int32_t *d_in, int32_t *d_out, size_t batch,
                     bool permute_out, cudaStream_t st);
 

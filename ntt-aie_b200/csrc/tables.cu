@@ -99,6 +99,29 @@ __global__ void reduce_kernel(const int32_t *in, int32_t *out, size_t count, uin
     for (size_t v = count4 * 4 + i; v < count; v += stride) out[v] = red(in[v]);
 }
 
+// out[b][i] = in[b][bitrev_logn(i)]; in place (in == out) as swaps of the pairs i < bitrev(i).
+// The standalone form of the bit-reversal adapter for the kernels that do not
+// fuse it into their load/store: one extra pass.
+__global__ void bitrev_permute_kernel(const int32_t *in, int32_t *out, uint32_t logn, uint64_t total) {
+    const uint32_t mask = (1u << logn) - 1u;
+    const bool in_place = in == out;
+    for (uint64_t t = (uint64_t) blockIdx.x * blockDim.x + threadIdx.x; t < total;
+         t += (uint64_t) gridDim.x * blockDim.x) {
+        const uint32_t i = (uint32_t) t & mask;
+        const uint32_t r = __brev(i) >> (32 - logn);
+        const uint64_t base = t - i;
+        if (in_place) {
+            if (i < r) {
+                const int32_t x = out[base + i], y = out[base + r];
+                out[base + i] = y;
+                out[base + r] = x;
+            }
+        } else {
+            out[t] = in[base + r];
+        }
+    }
+}
+
 static int grid_1d(uint64_t items, int sm_count) {
     uint64_t blocks = (items + 255) / 256;
     uint64_t cap = (uint64_t) sm_count * 16;
@@ -165,6 +188,16 @@ int build_tile_table(nttb200_plan *p) {
     const uint32_t chunks = p->n >> 12;
     tile_table_kernel<<<grid_1d((uint64_t) chunks * 32 * 65, p->sm_count), 256>>>(p->d_tw, p->d_tw_tile,
                                                                                   p->n, chunks);
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+    NTTB200_CUDA(cudaGetLastError());
+    return NTTB200_OK;
+}
+
+int launch_bitrev_permute(nttb200_plan *p, const int32_t *in, int32_t *out, size_t batch,
+                          cudaStream_t st) {
+    if (batch == 0) return NTTB200_OK;
+    const uint64_t total = (uint64_t) batch << p->logn;
+    bitrev_permute_kernel<<<grid_1d(total, p->sm_count), 256, 0, st>>>(in, out, p->logn, total);
     g_launches.fetch_add(1, std::memory_order_relaxed);
     NTTB200_CUDA(cudaGetLastError());
     return NTTB200_OK;

@@ -52,7 +52,7 @@ def _load_port():
         lib.oracle_powmod.restype = ctypes.c_int32
         lib.oracle_powmod.argtypes = [ctypes.c_int32, ctypes.c_int64, ctypes.c_int32]
         lib.oracle_make_roots.argtypes = [ctypes.c_int32, _i32p, ctypes.c_int32, ctypes.c_int32]
-        for name in ("oracle_ntt_gs", "oracle_ntt_ct"):
+        for name in ("oracle_ntt_gs", "oracle_ntt_ct", "oracle_ntt_gs_wide", "oracle_ntt_ct_wide"):
             getattr(lib, name).argtypes = [_i32p, ctypes.c_int32, _i32p, ctypes.c_int32,
                                            ctypes.c_int32]
         lib.oracle_pointwise.argtypes = [_i32p, _i32p, _i32p, ctypes.c_int64, ctypes.c_int32]
@@ -115,8 +115,31 @@ def ntt_gs(a: np.ndarray, roots: np.ndarray, p: int, stage: int = -1) -> np.ndar
     n = a.shape[-1]
     flat = a.reshape(-1, n)
     lib = _load_port()
+    # p > 2^30 is outside the golden's int32 domain: widened restatement (parity unpinned)
+    fn = lib.oracle_ntt_gs_wide if p > (1 << 30) else lib.oracle_ntt_gs
     for row in flat:
-        lib.oracle_ntt_gs(_ptr(row), n, _ptr(roots), p, stage)
+        fn(_ptr(row), n, _ptr(roots), p, stage)
+    return a
+
+
+def ntt_gs_wide(a: np.ndarray, roots: np.ndarray, p: int, stage: int = -1) -> np.ndarray:
+    """The widened (64-bit sums) form of the golden network for ANY p < 2^31."""
+    a = np.ascontiguousarray(a, dtype=np.int32).copy()
+    roots = np.ascontiguousarray(roots, dtype=np.int32)
+    n = a.shape[-1]
+    lib = _load_port()
+    for row in a.reshape(-1, n):
+        lib.oracle_ntt_gs_wide(_ptr(row), n, _ptr(roots), p, stage)
+    return a
+
+
+def ntt_ct_wide(a: np.ndarray, table: np.ndarray, p: int, stage: int = -1) -> np.ndarray:
+    a = np.ascontiguousarray(a, dtype=np.int32).copy()
+    table = np.ascontiguousarray(table, dtype=np.int32)
+    n = a.shape[-1]
+    lib = _load_port()
+    for row in a.reshape(-1, n):
+        lib.oracle_ntt_ct_wide(_ptr(row), n, _ptr(table), p, stage)
     return a
 
 
@@ -125,8 +148,9 @@ def ntt_ct(a: np.ndarray, table: np.ndarray, p: int, stage: int = -1) -> np.ndar
     table = np.ascontiguousarray(table, dtype=np.int32)
     n = a.shape[-1]
     lib = _load_port()
+    fn = lib.oracle_ntt_ct_wide if p > (1 << 30) else lib.oracle_ntt_ct
     for row in a.reshape(-1, n):
-        lib.oracle_ntt_ct(_ptr(row), n, _ptr(table), p, stage)
+        fn(_ptr(row), n, _ptr(table), p, stage)
     return a
 
 

@@ -128,6 +128,66 @@ ORACLE_API void oracle_ntt_ct(int32_t *a, int32_t n, const int32_t *table, int32
     }
 }
 
+/* ------------------------------------------------------------------ */
+/* WIDE moduli, 2^30 < p < 2^31 -- OUTSIDE the reference's domain       */
+/* (its int32 sums v0 + v1 and v0 + p - v1 at src/test.cpp:48-49        */
+/* overflow there), so parity for this range is UNPINNED upstream.      */
+/* Same loops as oracle_ntt_gs / oracle_ntt_ct with every sum widened   */
+/* to 64 bit; the tests assert that the two forms agree wherever the    */
+/* int32 form is defined (p <= 2^30) and check the wide range against   */
+/* Python big-integer arithmetic and the schoolbook product.            */
+/* ------------------------------------------------------------------ */
+ORACLE_API void oracle_ntt_gs_wide(int32_t *a, int32_t n, const int32_t *roots_rev, int32_t p,
+                                   int32_t stage) {
+    const uint64_t q = (uint64_t) (uint32_t) p;
+    int32_t t = 1;
+    int idx = 0;
+    for (int m = n; m > 1; m >>= 1) {
+        int32_t j1 = 0;
+        int32_t h = m / 2;
+        for (int i = 0; i < h; i++) {
+            int32_t j2 = j1 + t - 1;
+            uint64_t root = (uint64_t) (uint32_t) roots_rev[h + i];
+            for (int j = j1; j <= j2; j++) {
+                uint64_t v0 = (uint64_t) (uint32_t) a[j];
+                uint64_t v1 = (uint64_t) (uint32_t) a[j + t];
+                a[j] = (int32_t) ((v0 + v1) % q);
+                a[j + t] = (int32_t) ((((v0 + q - v1) % q) * root) % q);
+            }
+            j1 += 2 * t;
+        }
+        t <<= 1;
+        if (idx == stage) {
+            return;
+        }
+        idx += 1;
+    }
+}
+
+ORACLE_API void oracle_ntt_ct_wide(int32_t *a, int32_t n, const int32_t *table, int32_t p,
+                                   int32_t stage) {
+    const uint64_t q = (uint64_t) (uint32_t) p;
+    int32_t t = n;
+    int idx = 0;
+    for (int m = 1; m < n; m <<= 1) {
+        t >>= 1;
+        for (int i = 0; i < m; i++) {
+            int32_t j1 = 2 * i * t;
+            uint64_t s = (uint64_t) (uint32_t) table[m + i];
+            for (int j = j1; j < j1 + t; j++) {
+                uint64_t u = (uint64_t) (uint32_t) a[j];
+                uint64_t v = ((uint64_t) (uint32_t) a[j + t] * s) % q;
+                a[j] = (int32_t) ((u + v) % q);
+                a[j + t] = (int32_t) ((u + q - v) % q);
+            }
+        }
+        if (idx == stage) {
+            return;
+        }
+        idx += 1;
+    }
+}
+
 /* c[i] = a[i]*b[i] mod p ; c[i] = a[i]*s mod p  (new operators, see above) */
 ORACLE_API void oracle_pointwise(const int32_t *a, const int32_t *b, int32_t *c, int64_t count,
                                  int32_t p) {

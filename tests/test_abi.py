@@ -50,7 +50,8 @@ def test_argument_validation_without_device(lib):
     h = ctypes.c_void_p()
     ptr = roots.ctypes.data_as(ctypes.POINTER(ctypes.c_int32))
     assert L.nttb200_plan_create(ctypes.byref(h), 0, 0, 17, ptr, 0) == 1      # logn out of range
-    assert L.nttb200_plan_create(ctypes.byref(h), 0, 4, (1 << 30) + 1, ptr, 0) == 2  # modulus
+    assert L.nttb200_plan_create(ctypes.byref(h), 0, 4, 1 << 31, ptr, 0) == 2  # modulus >= 2^31
+    assert L.nttb200_plan_create(ctypes.byref(h), 0, 4, 1, ptr, 0) == 2
     assert L.nttb200_plan_create(ctypes.byref(h), 0, 4, 5, ptr, 0) == 3       # entry >= q
     assert L.nttb200_plan_create(ctypes.byref(h), 0, 3, 17, ptr, 1) == 1      # AIE order needs N>=16
     assert L.nttb200_gs_batch(None, None, None, 1, -1, None) == 1

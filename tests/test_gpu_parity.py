@@ -758,3 +758,98 @@ def test_polymul4096_one_kernel(lib, oracle_mod):
             for _ in range(3):
                 lib.polymul_negacyclic(pf, pi, d_a, d_b, d_c, big)
             assert np.array_equal(d_c.cpu().numpy(), want)
+
+
+@pytest.mark.parametrize("logn", [3, 9, 12, 14, 17])
+def test_wide_moduli(lib, oracle_mod, logn):
+    """2^30 < q < 2^31 (outside the reference's int32 domain; oracle = the
+    widened restatement).  GS with arbitrary tables, CT, partial depth, AIE order, the
+    negacyclic product and pointwise/scale, at an NTT prime (15*2^27+1), the Mersenne prime
+    2^31-1 and 2^30+3; inputs pinned at q-1."""
+    n = 1 << logn
+    rng = np.random.default_rng(21000 + logn)
+    for q in (2013265921, 2147483647, (1 << 30) + 3):
+        table = rng.integers(0, q, n, dtype=np.int64).astype(np.int32)
+        a = rng.integers(0, q, (3, n), dtype=np.int64).astype(np.int32)
+        a[0] = q - 1
+        table[1::2] = q - 1
+        out, path = run_gs(lib, a, table, q)
+        assert path == "generic_stage_pass"
+        assert np.array_equal(out, oracle_mod.ntt_gs(a, table, q)), (logn, q)
+        out, _ = run_gs(lib, a, table, q, stage=logn // 2, inplace=True)
+        assert np.array_equal(out, oracle_mod.ntt_gs(a, table, q, logn // 2)), (logn, q, "partial")
+        d_in = dev(a)
+        d_out = torch.empty_like(d_in)
+        with lib.Plan(logn, q, table) as plan:
+            plan.ct(d_in, d_out, 3)
+            assert np.array_equal(d_out.cpu().numpy(), oracle_mod.ntt_ct(a, table, q)), (logn, q, "ct")
+            b = rng.integers(0, q, (3, n), dtype=np.int64).astype(np.int32)
+            plan.pointwise(d_in, dev(b), d_out, 3 * n)
+            assert np.array_equal(d_out.cpu().numpy(), oracle_mod.pointwise(a, b, q))
+            plan.scale(d_in, d_out, 3 * n, q - 2)
+            assert np.array_equal(d_out.cpu().numpy(), oracle_mod.scale(a, q - 2, q))
+        if logn >= 4:
+            out, _ = run_gs(lib, a, table, q, flags=1)
+            assert np.array_equal(out, oracle_mod.ans_order_permute(oracle_mod.ntt_gs(a, table, q)))
+    # negacyclic product at the NTT prime 2013265921 (primitive root 31)
+    q, g = 2013265921, 31
+    fwd, inv = lib.negacyclic_tables(n, q, g)
+    a = rng.integers(0, q, (2, n), dtype=np.int64).astype(np.int32)
+    b = rng.integers(0, q, (2, n), dtype=np.int64).astype(np.int32)
+    prod = oracle_mod.pointwise(oracle_mod.ntt_ct(a, fwd, q), oracle_mod.ntt_ct(b, fwd, q), q)
+    want = oracle_mod.scale(oracle_mod.ntt_gs(prod, inv, q), pow(n, q - 2, q), q)
+    if logn <= 9:
+        assert np.array_equal(want[0], oracle_mod.negacyclic_schoolbook(a[0], b[0], q))
+    with lib.Plan(logn, q, fwd) as pf, lib.Plan(logn, q, inv) as pi:
+        d_c = torch.empty(2, n, dtype=torch.int32, device="cuda")
+        lib.polymul_negacyclic(pf, pi, dev(a), dev(b), d_c, 2)
+        assert np.array_equal(d_c.cpu().numpy(), want), logn
+    # generated tables on the wide range
+    w = lib.powmod(g, (q - 1) // n, q)
+    with lib.Plan.generated(logn, q, lib.GEN_POWERS, w) as plan:
+        assert np.array_equal(plan.table(), lib.make_roots(n, q, g))
+
+
+def _bitrev_index(n):
+    logn = n.bit_length() - 1
+    idx = np.arange(n)
+    rev = np.zeros(n, dtype=np.int64)
+    for b in range(logn):
+        rev |= ((idx >> b) & 1) << (logn - 1 - b)
+    return rev
+
+
+@pytest.mark.parametrize("logn", [1, 5, 11, 12, 13, 16])
+def test_bitrev_layout_adapters(lib, oracle_mod, logn):
+    """input stored in bit-reversed order / output delivered in bit-reversed
+    order.  At N = 4096 both adapters are fused into the golden kernel's load and store
+    (path fused_gs4096_tma_bitrev); elsewhere they are one permutation pass.  Also the
+    standalone permutation, out of place and in place, and the forward network."""
+    n = 1 << logn
+    rev = _bitrev_index(n)
+    rng = np.random.default_rng(22000 + logn)
+    table = rng.integers(0, Q29, n, dtype=np.int32)
+    a = rng.integers(0, Q29, (11, n), dtype=np.int32)
+    a[0] = np.arange(n) % Q29
+    want = oracle_mod.ntt_gs(a, table, Q29)
+    for flags, src, exp in ((lib.OUTPUT_BITREV, a, want[:, rev]),
+                            (lib.INPUT_BITREV, a[:, rev], want),
+                            (lib.INPUT_BITREV | lib.OUTPUT_BITREV, a[:, rev], want[:, rev])):
+        for inplace in (False, True):
+            out, path = run_gs(lib, src, table, Q29, flags=flags, inplace=inplace)
+            assert np.array_equal(out, exp), (logn, flags, inplace, path)
+            if logn == 12:
+                assert path == "fused_gs4096_tma_bitrev"
+        out, _ = run_gs(lib, src, table, Q29, flags=flags | lib.FORCE_GENERIC)
+        assert np.array_equal(out, exp), (logn, flags, "generic")
+    with lib.Plan(logn, Q29, table, flags=lib.OUTPUT_BITREV) as plan:
+        d_in, d_out = dev(a), torch.empty(11, n, dtype=torch.int32, device="cuda")
+        plan.ct(d_in, d_out, 11)
+        assert np.array_equal(d_out.cpu().numpy(), oracle_mod.ntt_ct(a, table, Q29)[:, rev])
+        plan.bitrev_permute(d_in, d_out, 11)
+        assert np.array_equal(d_out.cpu().numpy(), a[:, rev])
+        plan.bitrev_permute(d_in, d_in, 11)
+        assert np.array_equal(d_in.cpu().numpy(), a[:, rev])
+    if logn >= 4:
+        with pytest.raises(lib.NttError):
+            lib.Plan(logn, Q29, table, flags=lib.OUTPUT_BITREV | lib.ORDER_AIE_DEVICE)

@@ -196,3 +196,49 @@ def test_unreduced_fixture_matches_restatement():
         assert np.array_equal(oracle.ntt_gs(a, g[f"roots_{n}"], 3329), g[f"out_{n}"])
     a = (g["a_q29"].astype(np.int64) % 469762049).astype(np.int32)
     assert np.array_equal(oracle.ntt_gs(a, g["roots_q29"], 469762049), g["out_q29"])
+
+
+def test_wide_modulus_restatement(oracle_mod):
+    """2^30 < p < 2^31 is outside the golden's int32 domain (src/test.cpp:48-49 overflow):
+    the widened restatement (a) equals the int32 form wherever that is defined, (b) equals
+    Python big-integer arithmetic on the wide range, (c) GS(inv) o CT(fwd) = n * identity and
+    the negacyclic product equals the schoolbook product at p = 2013265921 = 15*2^27 + 1."""
+    rng = np.random.default_rng(77)
+    for p in (3329, 469762049, 1 << 30):
+        for n in (2, 64, 1024):
+            table = rng.integers(0, p, n, dtype=np.int32)
+            a = rng.integers(0, p, (2, n), dtype=np.int32)
+            assert np.array_equal(oracle_mod.ntt_gs_wide(a, table, p), oracle_mod.ntt_gs(a, table, p))
+            assert np.array_equal(oracle_mod.ntt_ct_wide(a, table, p), oracle_mod.ntt_ct(a, table, p))
+
+    def gs_python(a, table, p):
+        a = [int(x) for x in a]
+        n, t, m = len(a), 1, len(a)
+        while m > 1:
+            h = m // 2
+            for i in range(h):
+                for j in range(2 * i * t, 2 * i * t + t):
+                    v0, v1 = a[j], a[j + t]
+                    a[j] = (v0 + v1) % p
+                    a[j + t] = ((v0 + p - v1) % p) * int(table[h + i]) % p
+            t, m = t * 2, h
+        return np.array(a, dtype=np.int64)
+
+    for p in (2013265921, 2147483647, (1 << 30) + 3):
+        n = 256
+        table = rng.integers(0, p, n, dtype=np.int64).astype(np.int32)
+        a = rng.integers(0, p, n, dtype=np.int64).astype(np.int32)
+        a[:4] = p - 1
+        assert np.array_equal(oracle_mod.ntt_gs(a, table, p).astype(np.int64), gs_python(a, table, p))
+    p, n, g = 2013265921, 512, 31
+    psi = pow(g, (p - 1) // (2 * n), p)
+    assert pow(psi, n, p) == p - 1
+    fwd = oracle_mod.make_bitrev_table(n, p, psi)
+    inv = oracle_mod.make_bitrev_table(n, p, pow(psi, p - 2, p))
+    a = rng.integers(0, p, (2, n), dtype=np.int64).astype(np.int32)
+    b = rng.integers(0, p, (2, n), dtype=np.int64).astype(np.int32)
+    assert np.array_equal(oracle_mod.ntt_gs(oracle_mod.ntt_ct(a, fwd, p), inv, p),
+                          oracle_mod.scale(a, n, p))
+    prod = oracle_mod.pointwise(oracle_mod.ntt_ct(a, fwd, p), oracle_mod.ntt_ct(b, fwd, p), p)
+    c = oracle_mod.scale(oracle_mod.ntt_gs(prod, inv, p), pow(n, p - 2, p), p)
+    assert np.array_equal(c[0], oracle_mod.negacyclic_schoolbook(a[0], b[0], p))
