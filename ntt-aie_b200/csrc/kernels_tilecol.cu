@@ -401,6 +401,14 @@ int launch_tilecol_gs(nttb200_plan *p, const int32_t *d_in, const int32_t *d_b, 
     if (logg < 1 || logg > 4 || !p->d_tw_tile || !tilecol_enabled(p->logn)) return NTTB200_ERR_UNSUPPORTED;
     const uint64_t tiles = (uint64_t) batch << logg;
     if (tiles > 0x7fffffffull || ((uintptr_t) d_out & 15u)) return NTTB200_ERR_UNSUPPORTED;
+    // below ~14 tiles per team the prologue, the lag and the drain phase cost more than the
+    // saved HBM pass (measured at N = 2^16: 512 polynomials 0.199 ms against 0.12 ms for the
+    // two passes, 1024 polynomials 0.214 against 0.227, 4096 polynomials 0.748 against 0.814)
+    static const long min_per_team = []() {
+        const char *e = getenv("NTTB200_TILECOL_MIN_TILES_PER_TEAM");
+        return e ? atol(e) : 12L;
+    }();
+    if (tiles < (uint64_t) p->sm_count * kM_Teams * (uint64_t) min_per_team) return NTTB200_ERR_UNSUPPORTED;
     CUtensorMap a_lo, a_hi, b_lo, b_hi;
     if (tile_maps(&a_lo, &a_hi, d_in, (size_t) tiles) != NTTB200_OK) return NTTB200_ERR_UNSUPPORTED;
     TileColParams tp;

@@ -116,15 +116,24 @@ class SymmetricBuffers:
         import torch.distributed._symmetric_memory as symm_mem
         grp = group if group is not None else dist.group.WORLD
         dev = torch.device("cuda", device)
-        self.scratch = symm_mem.empty(shard_len, dtype=torch.int32, device=dev)
-        self.final = symm_mem.empty(shard_len, dtype=torch.int32, device=dev)
-        self.h_scratch = symm_mem.rendezvous(self.scratch, grp)
-        self.h_final = symm_mem.rendezvous(self.final, grp)
-        self.scratch_ptrs = [int(p) for p in self.h_scratch.buffer_ptrs]
-        self.final_ptrs = [int(p) for p in self.h_final.buffer_ptrs]
+        # TWO sets, alternated per call: a peer that has already entered call k+1 scatters
+        # into the other set while this rank may still read its result of call k; it cannot
+        # be two calls ahead because every call contains barriers all ranks take part in.
+        self.scratch, self.final, self.scratch_ptrs, self.final_ptrs = [], [], [], []
+        self.handles = []
+        for _ in range(2):
+            sc = symm_mem.empty(shard_len, dtype=torch.int32, device=dev)
+            fi = symm_mem.empty(shard_len, dtype=torch.int32, device=dev)
+            hs, hf = symm_mem.rendezvous(sc, grp), symm_mem.rendezvous(fi, grp)
+            self.scratch.append(sc)
+            self.final.append(fi)
+            self.handles += [hs, hf]
+            self.scratch_ptrs.append([int(p) for p in hs.buffer_ptrs])
+            self.final_ptrs.append([int(p) for p in hf.buffer_ptrs])
+        self.calls = 0
 
     def barrier(self) -> None:
-        self.h_scratch.barrier(channel=0)
+        self.handles[0].barrier(channel=0)
 
 
 class FourStepNTT:
@@ -192,20 +201,22 @@ class FourStepNTT:
 
     def _forward_fused(self, shard, natural_order: bool):
         """Steps 1-4 with both transposes fused into the passes' stores.  Returns the
-        symmetric buffer that holds the result.  The result must be consumed on every rank
-        before any rank calls forward() again: the entry barrier below keeps a faster peer
-        from scattering its next step-1 results into a buffer this rank still reads."""
+        symmetric buffer that holds the result; it stays valid until the call AFTER the next
+        one (the receive buffers are double-buffered, see SymmetricBuffers), so a rank may
+        still read its result while a faster peer has already started the next transform."""
         eng, sy = self.engine, self.symm
         logc = self.logs - (self.world.bit_length() - 1)
-        sy.barrier()                      # every rank is done with the previous call's buffers
+        k = sy.calls & 1
+        sy.calls += 1
+        scratch, final = sy.scratch[k], sy.final[k]
         # steps 1+2: local stages; the last pass scatters into every rank's scratch
-        eng.plan_local.gs_stage_range_scatter(shard, 0, self.logs, sy.scratch_ptrs, self.rank)
+        eng.plan_local.gs_stage_range_scatter(shard, 0, self.logs, sy.scratch_ptrs[k], self.rank)
         sy.barrier()                      # all slices have landed everywhere
         if not natural_order:
-            eng.plan_cross.gs_stage_range(sy.scratch, sy.scratch, 1, logc, self.logs)   # step 3
-            sy.barrier()                  # peers may overwrite scratch only after this
-            return sy.scratch
+            eng.plan_cross.gs_stage_range(scratch, scratch, 1, logc, self.logs)   # step 3
+            sy.barrier()                  # keeps the ranks within one call of each other
+            return scratch
         # steps 3+4: cross-GPU stages; their results go straight home
-        eng.plan_cross.gs_stage_range_scatter(sy.scratch, logc, self.logs, sy.final_ptrs, self.rank)
+        eng.plan_cross.gs_stage_range_scatter(scratch, logc, self.logs, sy.final_ptrs[k], self.rank)
         sy.barrier()
-        return sy.final
+        return final

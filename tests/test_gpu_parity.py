@@ -853,3 +853,41 @@ def test_bitrev_layout_adapters(lib, oracle_mod, logn):
     if logn >= 4:
         with pytest.raises(lib.NttError):
             lib.Plan(logn, Q29, table, flags=lib.OUTPUT_BITREV | lib.ORDER_AIE_DEVICE)
+
+
+def test_persistent_tile_column_kernel_full_batch(lib, oracle_mod):
+    """N = 2^16 with a batch large enough for the persistent tile-item / column-item kernel
+    (kernels_tilecol.cu; smaller batches take the two passes): sampled rows against the oracle,
+    linearity over the whole batch, in place, and the product tail (DUAL) via polymul."""
+    logn, batch = 16, 1000
+    n = 1 << logn
+    rng = np.random.default_rng(23000)
+    table = rng.integers(0, Q29, n, dtype=np.int32)
+    gen = torch.Generator(device="cuda").manual_seed(23000)
+    a = torch.randint(0, Q29, (batch, n), dtype=torch.int32, device="cuda", generator=gen)
+    fa, f2 = torch.empty_like(a), torch.empty_like(a)
+    with lib.Plan(logn, Q29, table) as plan:
+        plan.gs(a, fa, batch)
+        torch.cuda.synchronize()
+        assert "tilecol" in plan.last_path, plan.last_path
+        a2 = ((a.to(torch.int64) * 3) % Q29).to(torch.int32)
+        plan.gs(a2, f2, batch)
+        assert torch.equal(f2.to(torch.int64), (fa.to(torch.int64) * 3) % Q29)
+        idx = [0, 1, 499, batch - 1] + rng.integers(0, batch, 4).tolist()
+        assert np.array_equal(fa[idx].cpu().numpy(), oracle_mod.ntt_gs(a[idx].cpu().numpy(), table, Q29))
+        plan.gs(a2, a2, batch)                      # in place
+        assert torch.equal(a2, f2)
+    fwd, inv = lib.negacyclic_tables(n, Q29, 3)
+    b = torch.randint(0, Q29, (batch, n), dtype=torch.int32, device="cuda", generator=gen)
+    b[0].zero_()
+    b[0, 5] = 1                                      # x^5: a negacyclic shift
+    with lib.Plan(logn, Q29, fwd) as pf, lib.Plan(logn, Q29, inv) as pi:
+        lib.polymul_negacyclic(pf, pi, a, b, fa, batch)
+        assert "tilecol" in pi.last_path, pi.last_path
+    a0 = a[0].to(torch.int64)
+    assert torch.equal(fa[0].to(torch.int64), torch.cat([(Q29 - a0[n - 5:]) % Q29, a0[:n - 5]]))
+    i = batch - 1
+    av, bv = a[i:i + 1].cpu().numpy(), b[i:i + 1].cpu().numpy()
+    prod = oracle_mod.pointwise(oracle_mod.ntt_ct(av, fwd, Q29), oracle_mod.ntt_ct(bv, fwd, Q29), Q29)
+    want = oracle_mod.scale(oracle_mod.ntt_gs(prod, inv, Q29), oracle_mod.powmod(n, Q29 - 2, Q29), Q29)
+    assert np.array_equal(fa[i:i + 1].cpu().numpy(), want)
