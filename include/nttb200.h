@@ -191,6 +191,13 @@ NTTB200_API int nttb200_gs_host(nttb200_plan *plan, const int32_t *h_in, int32_t
 NTTB200_API int nttb200_bitrev_permute(nttb200_plan *plan, const int32_t *d_in, int32_t *d_out,
                                        size_t batch, void *cuda_stream);
 
+/* Layout adapter: batch-major [batch][N] (this library's layout, the reference's flat buffer
+ * object per transform) <-> batch-minor [N][batch] (coefficient i of polynomial b at
+ * i*batch + b).  to_batch_minor != 0: d_in is [batch][N], d_out becomes [N][batch]; 0: the
+ * reverse.  One transposing pass, out of place (d_in != d_out). */
+NTTB200_API int nttb200_transpose(nttb200_plan *plan, const int32_t *d_in, int32_t *d_out,
+                                  size_t batch, int to_batch_minor, void *cuda_stream);
+
 /* out[i] = in[i] mod q in [0, q) for ANY int32 words (device pointers): the reduction the
  * golden applies with `%` when it first touches an input (src/test.cpp:46-50). */
 NTTB200_API int nttb200_reduce(nttb200_plan *plan, const int32_t *d_in, int32_t *d_out,

@@ -62,6 +62,7 @@ def load_library():
         "nttb200_plan_table": (ctypes.c_int, [vp, _i32p]),
         "nttb200_reduce": (ctypes.c_int, [vp, vp, vp, sz, vp]),
         "nttb200_bitrev_permute": (ctypes.c_int, [vp, vp, vp, sz, vp]),
+        "nttb200_transpose": (ctypes.c_int, [vp, vp, vp, sz, ctypes.c_int, vp]),
         "nttb200_gs_batch": (ctypes.c_int, [vp, vp, vp, sz, ctypes.c_int, vp]),
         "nttb200_ct_batch": (ctypes.c_int, [vp, vp, vp, sz, ctypes.c_int, vp]),
         "nttb200_gs_stage_range": (ctypes.c_int, [vp, vp, vp, sz, ctypes.c_int, ctypes.c_int, vp]),
@@ -99,7 +100,7 @@ def load_library():
 EXPORTED_SYMBOLS = (
     "nttb200_make_roots", "nttb200_make_bitrev_table", "nttb200_powmod", "nttb200_plan_create",
     "nttb200_plan_destroy", "nttb200_plan_create_generated", "nttb200_plan_table", "nttb200_reduce",
-    "nttb200_bitrev_permute",
+    "nttb200_bitrev_permute", "nttb200_transpose",
     "nttb200_gs_batch", "nttb200_ct_batch", "nttb200_gs_stage_range",
     "nttb200_gs_host", "nttb200_gs_stage_range_scatter", "nttb200_host_alloc", "nttb200_host_free",
     "nttb200_pointwise", "nttb200_scale", "nttb200_polymul_negacyclic",
@@ -261,6 +262,11 @@ class Plan:
         """out[b][i] = in[b][bitrev(i)] (in place allowed)."""
         _check(self._lib.nttb200_bitrev_permute(self._h, _addr(d_in), _addr(d_out), batch,
                                                 _stream(stream)), "bitrev_permute")
+
+    def transpose(self, d_in, d_out, batch: int, to_batch_minor: bool, stream=None) -> None:
+        """[batch][N] -> [N][batch] (to_batch_minor) or back; out of place."""
+        _check(self._lib.nttb200_transpose(self._h, _addr(d_in), _addr(d_out), batch,
+                                           1 if to_batch_minor else 0, _stream(stream)), "transpose")
 
     def reduce(self, d_in, d_out, count: int, stream=None) -> None:
         """out = in mod q for arbitrary int32 words (the golden's `%` on first touch)."""

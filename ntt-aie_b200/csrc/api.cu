@@ -422,6 +422,14 @@ int nttb200_bitrev_permute(nttb200_plan *p, const int32_t *d_in, int32_t *d_out,
     return launch_bitrev_permute(p, d_in, d_out, batch, (cudaStream_t) stream);
 }
 
+int nttb200_transpose(nttb200_plan *p, const int32_t *d_in, int32_t *d_out, size_t batch,
+                      int to_batch_minor, void *stream) {
+    if (!p || (batch && (!d_in || !d_out || d_in == d_out))) return NTTB200_ERR_INVALID_ARG;
+    DeviceGuard guard(p->device);
+    return to_batch_minor ? launch_transpose(p, d_in, d_out, batch, p->n, (cudaStream_t) stream)
+                          : launch_transpose(p, d_in, d_out, p->n, batch, (cudaStream_t) stream);
+}
+
 int nttb200_gs_stage_range(nttb200_plan *p, const int32_t *d_in, int32_t *d_out, size_t batch,
                            int stage_begin, int stage_end, void *stream) {
     if (!p || (batch && (!d_in || !d_out))) return NTTB200_ERR_INVALID_ARG;

@@ -87,6 +87,8 @@ int build_generated_table(nttb200_plan *p, uint32_t kind, uint32_t base, uint32_
 int build_tile_table(nttb200_plan *p);
 int launch_bitrev_permute(nttb200_plan *p, const int32_t *in, int32_t *out, size_t batch,
                           cudaStream_t st);
+int launch_transpose(nttb200_plan *p, const int32_t *in, int32_t *out, uint64_t rows, uint64_t cols,
+                     cudaStream_t st);
 int launch_reduce(nttb200_plan *p, const int32_t *in, int32_t *out, size_t count, cudaStream_t st);
 
 // N = 2^13..2^15 in one pass, private twiddles in tensor memory (kernels_poly.cu)

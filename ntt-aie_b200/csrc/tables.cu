@@ -122,6 +122,27 @@ __global__ void bitrev_permute_kernel(const int32_t *in, int32_t *out, uint32_t 
     }
 }
 
+// out[c][r] = in[r][c] for a rows x cols int32 matrix (32 x 32 tiles through shared memory,
+// both sides coalesced): batch-major [batch][N] <-> batch-minor [N][batch].
+__global__ void transpose_kernel(const int32_t *__restrict__ in, int32_t *__restrict__ out,
+                                 uint64_t rows, uint64_t cols) {
+    __shared__ int32_t tile[32][33];
+    const uint64_t tiles_c = (cols + 31) / 32, tiles_r = (rows + 31) / 32;
+    for (uint64_t t = blockIdx.x; t < tiles_c * tiles_r; t += gridDim.x) {
+        const uint64_t tr = t / tiles_c, tc = t - tr * tiles_c;
+        for (int y = threadIdx.y; y < 32; y += blockDim.y) {
+            const uint64_t r = tr * 32 + y, c = tc * 32 + threadIdx.x;
+            if (r < rows && c < cols) tile[y][threadIdx.x] = in[r * cols + c];
+        }
+        __syncthreads();
+        for (int y = threadIdx.y; y < 32; y += blockDim.y) {
+            const uint64_t c = tc * 32 + y, r = tr * 32 + threadIdx.x;
+            if (r < rows && c < cols) out[c * rows + r] = tile[threadIdx.x][y];
+        }
+        __syncthreads();
+    }
+}
+
 static int grid_1d(uint64_t items, int sm_count) {
     uint64_t blocks = (items + 255) / 256;
     uint64_t cap = (uint64_t) sm_count * 16;
@@ -198,6 +219,17 @@ int launch_bitrev_permute(nttb200_plan *p, const int32_t *in, int32_t *out, size
     if (batch == 0) return NTTB200_OK;
     const uint64_t total = (uint64_t) batch << p->logn;
     bitrev_permute_kernel<<<grid_1d(total, p->sm_count), 256, 0, st>>>(in, out, p->logn, total);
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+    NTTB200_CUDA(cudaGetLastError());
+    return NTTB200_OK;
+}
+
+int launch_transpose(nttb200_plan *p, const int32_t *in, int32_t *out, uint64_t rows, uint64_t cols,
+                     cudaStream_t st) {
+    if (rows == 0 || cols == 0) return NTTB200_OK;
+    const uint64_t tiles = ((rows + 31) / 32) * ((cols + 31) / 32);
+    const uint64_t cap = (uint64_t) p->sm_count * 16;
+    transpose_kernel<<<(int) (tiles < cap ? tiles : cap), dim3(32, 8), 0, st>>>(in, out, rows, cols);
     g_launches.fetch_add(1, std::memory_order_relaxed);
     NTTB200_CUDA(cudaGetLastError());
     return NTTB200_OK;

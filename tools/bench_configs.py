@@ -85,6 +85,36 @@ def cfg1(reps):
                       "reference_npu_wall_us": 279, "reference_npu_kernel_us": 14.375}), flush=True)
 
 
+def exectime(reps, logns):
+    """The reference's own experiment (profile/exectime/ntt_*core_logn*.csv, plot_exectime.py):
+    wall time of ONE transform per host call -- here nttb200_gs_host on a page-locked buffer --
+    trimmed mean dropping min and max (plot_exectime.py:27-29), and the device time of the
+    same single transform (the reference's kernel time, plot_kerneltime.py)."""
+    import time
+    for logn in logns:
+        n = 1 << logn
+        roots = nt.make_roots(n, Q, 3)
+        a = np.random.default_rng(logn).integers(0, Q, n, dtype=np.int32)
+        out = np.empty_like(a)
+        with nt.Plan(logn, Q, roots) as plan:
+            plan.gs_host(a, out, 1)
+            ok = bool(np.array_equal(out, oracle.ntt_gs(a, roots, Q)))
+            us = []
+            for _ in range(max(reps, 30)):
+                t0 = time.perf_counter()
+                plan.gs_host(a, out, 1)
+                us.append((time.perf_counter() - t0) * 1e6)
+            d_in = torch.from_numpy(a).cuda()
+            d_out = torch.empty_like(d_in)
+            ms = time_launches(lambda: plan.gs(d_in, d_out, 1), reps)
+            path = plan.last_path
+        us.sort()
+        print(json.dumps({"config": f"exectime single transform N=2^{logn}", "logn": logn,
+                          "host_call_us_trimmed_mean": statistics.mean(us[1:-1]),
+                          "device_kernel_us_trimmed_mean": trimmed(ms) * 1e3, "kernel_path": path,
+                          "bit_exact": ok}), flush=True)
+
+
 def ntt_sweep(reps, logns):
     for logn in logns:
         n = 1 << logn
@@ -105,6 +135,29 @@ def ntt_sweep(reps, logns):
                           "polys_per_s": batch / t, "butterflies_per_s": batch * (n // 2) * logn / t,
                           "algorithmic_GBps": gbs, "frac_of_measured_hbm": gbs / peak(),
                           "ms": t * 1e3, "kernel_path": path, "bit_exact_sampled": ok}), flush=True)
+
+
+def ct_sweep(reps, logns):
+    """forward (Cooley-Tukey) partner of ntt_sweep"""
+    for logn in logns:
+        n = 1 << logn
+        batch = (1 << 26) // n
+        fwd, _ = nt.negacyclic_tables(n, Q, 3)
+        gen = torch.Generator(device="cuda").manual_seed(200 + logn)
+        d_in = torch.randint(0, Q, (batch, n), dtype=torch.int32, device="cuda", generator=gen)
+        d_out = torch.empty_like(d_in)
+        with nt.Plan(logn, Q, fwd) as plan:
+            ms = time_launches(lambda: plan.ct(d_in, d_out, batch), reps)
+            path = plan.last_path
+        idx = [0, batch - 1, batch // 2]
+        ok = bool(np.array_equal(d_out[idx].cpu().numpy(),
+                                 oracle.ntt_ct(d_in[idx].cpu().numpy(), fwd, Q)))
+        t = trimmed(ms) * 1e-3
+        gbs = batch * n * 8 / t / 1e9
+        print(json.dumps({"config": f"ntt forward CT N=2^{logn} batch={batch}", "logn": logn,
+                          "polys_per_s": batch / t, "algorithmic_GBps": gbs,
+                          "frac_of_measured_hbm": gbs / peak(), "ms": t * 1e3, "kernel_path": path,
+                          "bit_exact_sampled": ok}), flush=True)
 
 
 def cfg3(reps, logns=range(12, 17)):
@@ -193,14 +246,18 @@ def rns(reps):
 
 def main():
     ap = argparse.ArgumentParser()
-    ap.add_argument("--configs", default="1,ntt,3s,3,4,rns")
+    ap.add_argument("--configs", default="1,exectime,ntt,ct,3s,3,4,rns")
     ap.add_argument("--reps", type=int, default=20)
     args = ap.parse_args()
     todo = args.configs.split(",")
     if "1" in todo:
         cfg1(args.reps)
+    if "exectime" in todo:
+        exectime(args.reps, range(7, 17))
     if "ntt" in todo:
         ntt_sweep(args.reps, range(7, 17))  # the reference profiles logN 7..13
+    if "ct" in todo:
+        ct_sweep(args.reps, range(9, 17))
     if "3s" in todo:
         cfg3(args.reps, range(9, 12))      # below the BASELINE sweep: the reference's own N = 2048
     if "3" in todo:
