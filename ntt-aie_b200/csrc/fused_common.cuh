@@ -166,6 +166,31 @@ __device__ __forceinline__ void tmem_wait_st() {
     asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
 }
 
+// Fill one private-twiddle table (128 columns) of the calling warp's lanes from global
+// memory.  `src` points at element (slot 0, this thread's j) of a [32 slots][row_stride]
+// uint4 layout.  All 16 warps of the CTA take part: the four warps that share a lane quadrant
+// (warp, warp+4, ..) split the eight 16-column groups, two each, with eight loads in flight --
+// the prologue of a 150 us launch must not cost 30 us of serial L2 round trips.
+__device__ __forceinline__ void tmem_fill_table(uint32_t taddr_table, const uint4 *src, int row_stride,
+                                                int warp) {
+    const int s = warp >> 2;   // which two groups this warp writes
+    uint32_t r[2][16];
+#pragma unroll
+    for (int h = 0; h < 2; h++) {
+        const int g = s + 4 * h;
+#pragma unroll
+        for (int e = 0; e < 4; e++) {
+            const uint4 x = __ldg(src + (size_t) (4 * g + e) * row_stride);
+            r[h][4 * e + 0] = x.x;
+            r[h][4 * e + 1] = x.y;
+            r[h][4 * e + 2] = x.z;
+            r[h][4 * e + 3] = x.w;
+        }
+    }
+#pragma unroll
+    for (int h = 0; h < 2; h++) tmem_st16(taddr_table + 16u * (s + 4 * h), r[h]);
+}
+
 // NB consecutive blocks B0.. of stage S (pairs i, i + 2^S) with the (w, w') pairs of those
 // blocks in t[0..2*NB): the unit of work between two TMEM loads.
 template <int S, int B0, int NB, bool REDUCE>

@@ -47,23 +47,12 @@ __device__ __forceinline__ uint32_t poly_prologue(const uint4 *tw_tile, uint32_t
     tmem_fence_after_sync();
     tmem_base = lds32(tmem_slot);
     const uint32_t lane_base = tmem_base + ((uint32_t) (warp & 3) << 21);
-    if (warp < 4) {  // teams 0 and 1 cover all 128 lanes; lane half h holds positions of parity h
+    {   // lane half h (= quadrant / 2) holds the positions of parity h, 128 columns each
+        const int h = (warp & 3) >> 1;
 #pragma unroll 1
-        for (int pos = warp >> 1; pos < G; pos += 2) {
-            const uint4 *src = tw_tile + (size_t) pos * kM_TwTile + j;
-#pragma unroll 1
-            for (int g = 0; g < 8; g++) {
-                uint32_t r[16];
-#pragma unroll
-                for (int k = 0; k < 4; k++) {
-                    const uint4 x = __ldg(src + (4 * g + k) * kM_TwRow);
-                    r[4 * k + 0] = x.x;
-                    r[4 * k + 1] = x.y;
-                    r[4 * k + 2] = x.z;
-                    r[4 * k + 3] = x.w;
-                }
-                tmem_st16(lane_base + (uint32_t) (pos >> 1) * 128u + 16u * g, r);
-            }
+        for (int pos = h; pos < G; pos += 2) {
+            tmem_fill_table(lane_base + (uint32_t) (pos >> 1) * 128u,
+                            tw_tile + (size_t) pos * kM_TwTile + j, kM_TwRow, warp);
         }
         tmem_wait_st();
     }

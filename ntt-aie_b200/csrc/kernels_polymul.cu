@@ -118,24 +118,10 @@ polymul4096_kernel(const __grid_constant__ CUtensorMap a_lo, const __grid_consta
     const uint32_t tw_fwd = lane_base + kP_ColFwd, tw_inv = lane_base + kP_ColInv;
     const uint32_t park = lane_base + kP_ColPark + (uint32_t) (warp >> 2) * 64u;
 
-    // the four warps of teams 0 and 1 cover all 128 lanes: fill both private-twiddle tables
-    if (warp < 4) {
-#pragma unroll 1
-        for (int g = 0; g < 16; g++) {
-            const uint4 *src = (g < 8 ? prm.tw_fwd : prm.tw_inv) + (size_t) (g & 7) * 4 * kF_Team + j;
-            uint32_t r[16];
-#pragma unroll
-            for (int k = 0; k < 4; k++) {
-                const uint4 x = __ldg(src + k * kF_Team);
-                r[4 * k + 0] = x.x;
-                r[4 * k + 1] = x.y;
-                r[4 * k + 2] = x.z;
-                r[4 * k + 3] = x.w;
-            }
-            tmem_st16(lane_base + (g < 8 ? kP_ColFwd : kP_ColInv) + (uint32_t) (g & 7) * 16u, r);
-        }
-        tmem_wait_st();
-    }
+    // both private-twiddle tables, every warp its share of its own lanes
+    tmem_fill_table(lane_base + kP_ColFwd, prm.tw_fwd + j, kF_Team, warp);
+    tmem_fill_table(lane_base + kP_ColInv, prm.tw_inv + j, kF_Team, warp);
+    tmem_wait_st();
     tmem_fence_before_sync();
     __syncthreads();
     tmem_fence_after_sync();

@@ -121,24 +121,13 @@ tilecol_gs_kernel(const __grid_constant__ CUtensorMap map_lo, const __grid_const
     tmem_fence_after_sync();
     const uint32_t tmem_base = lds32(tmem_slot);
     const uint32_t lane_base = tmem_base + ((uint32_t) (warp & 3) << 21);
-    if (warp < 4) {  // lane half h holds the positions of parity h: columns k*128
+    {   // lane half h holds the positions of parity h: columns k*128
+        const uint32_t h = (uint32_t) (warp & 3) >> 1;
 #pragma unroll 1
         for (int k = 0; k < K; k++) {
-            const uint32_t pos = cta_half * 8 + 2 * k + (warp >> 1);
-            const uint4 *src = prm.tw_tile + (size_t) pos * kM_TwTile + j;
-#pragma unroll 1
-            for (int g = 0; g < 8; g++) {
-                uint32_t r[16];
-#pragma unroll
-                for (int e = 0; e < 4; e++) {
-                    const uint4 x = __ldg(src + (4 * g + e) * kM_TwRow);
-                    r[4 * e + 0] = x.x;
-                    r[4 * e + 1] = x.y;
-                    r[4 * e + 2] = x.z;
-                    r[4 * e + 3] = x.w;
-                }
-                tmem_st16(lane_base + (uint32_t) k * 128u + 16u * g, r);
-            }
+            const uint32_t pos = cta_half * 8 + 2 * k + h;
+            tmem_fill_table(lane_base + (uint32_t) k * 128u, prm.tw_tile + (size_t) pos * kM_TwTile + j,
+                            kM_TwRow, warp);
         }
         tmem_wait_st();
     }
