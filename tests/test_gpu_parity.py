@@ -273,7 +273,7 @@ def test_cpp_host_harness(lib):
         mod.build_host_harness()
     for extra in ([], ["--aie-order"], ["--logn", "12", "--p", "469762049", "--batch", "33",
                                         "--random", "--iters", "2"],
-                  ["--stage", "4"]):
+                  ["--stage", "4"], ["--logn", "12"], ["--logn", "13"]):   # a[i] = i >= p there
         res = subprocess.run([exe] + extra, capture_output=True, text=True, timeout=120)
         assert res.returncode == 0 and "PASS!" in res.stdout, res.stdout + res.stderr
 

@@ -1,27 +1,24 @@
 #!/bin/bash
-# ncu recipe behind profiles/ (run on a B200 box, e.g. `gpurun -- bash tools/profile_ncu.sh`).
+# ncu recipe behind profiles/ (run on a B200 box: `gpurun -- bash tools/profile_ncu.sh`).
 # Successor of the reference's trace tooling (event0/event1 markers + scripts/parse_trace.py +
-# profile/plot_*.py): launch list (per-launch device time; compare SHARES, the numbers are
-# cold-cache and serialised) and one `--set full` capture of the dominant kernel.
-# Outputs land in gpurun_out/; summarise with:
-#   ncu -i gpurun_out/prof_fused.ncu-rep --page raw --csv   (dram bytes, pipe utilisation, stalls)
-#   ncu -i gpurun_out/prof_fused.ncu-rep --page source --csv (per-instruction stall samples)
+# profile/plot_*.py): (1) the launch list of the bench command (per-launch device time; compare
+# SHARES, the numbers are cold-cache and serialised), (2) one `--set full` capture per kernel
+# family.  Every command is profiled only after the same command exited 0 without ncu.
+# Outputs land in gpurun_out/; summarise with tools/summarize_ncu.py (no GPU needed).
 set -u
 mkdir -p gpurun_out
-CMD="python bench.py --steps 5 --warmup 3 --no-cpu-baseline"
-# a command is profiled only after the same command exited 0 without ncu
+CMD="python bench.py --steps 5 --warmup 3 --no-cpu-baseline --no-e2e"
 $CMD > gpurun_out/plain.log 2>&1 || { echo "plain run failed"; exit 1; }
-ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv \
-    --log-file gpurun_out/launches.csv $CMD > /dev/null 2>&1
-CMD2="python bench.py --steps 5 --warmup 3 --no-e2e --no-cpu-baseline"
-$CMD2 > gpurun_out/plain2.log 2>&1 || { echo "plain run failed"; exit 1; }
-ncu --set full --clock-control none --import-source on -k regex:fused_gs4096 -s 3 -c 1 -f \
-    -o gpurun_out/prof_fused $CMD2 > gpurun_out/ncu_full.log 2>&1
-# secondary kernels (tile / column / CT / small-N), one launch each
-CMD3="python tools/bench_configs.py --reps 3 --configs ntt,3,4"
-$CMD3 > gpurun_out/plain3.log 2>&1 || { echo "plain run failed"; exit 1; }
-for k in tile_gs_kernel column_kernel tile_ct fused_gs_small_kernel poly_gs_kernel; do
-  ncu --set full --clock-control none --import-source on -k regex:$k -s 4 -c 1 -f \
-      -o gpurun_out/prof_$k $CMD3 > /dev/null 2>&1
-done
-ls -la gpurun_out/*.ncu-rep gpurun_out/launches.csv
+ncu --metrics gpu__time_duration.sum --clock-control none -c 800 --csv \
+    --log-file gpurun_out/launches_bench.csv $CMD > /dev/null 2>&1
+cap() {  # cap <target> <kernel regex> <report name>
+  python tools/dev/ncu_targets.py $1 > gpurun_out/plain_$1.log 2>&1 || { echo "plain $1 failed"; return; }
+  ncu --set full --clock-control none --import-source on -k regex:$2 -s 3 -c 1 -f \
+      -o gpurun_out/prof_$3 python tools/dev/ncu_targets.py $1 > gpurun_out/ncu_$3.log 2>&1
+}
+cap headline fused_gs4096 fused_gs4096
+cap polymul polymul4096 polymul4096
+cap poly15 polyt_gs polyt_gs15
+cap tilecol16 tilecol_gs tilecol_gs16
+cap ct4096 tile_ct_db tile_ct_db
+ls -la gpurun_out/*.ncu-rep gpurun_out/launches_bench.csv

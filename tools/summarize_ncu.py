@@ -16,6 +16,12 @@ KEYS = ['gpu__time_duration.sum', 'dram__bytes_read.sum', 'dram__bytes_write.sum
         'smsp__issue_active.avg.pct_of_peak_sustained_active',
         'sm__inst_executed_pipe_alu.avg.pct_of_peak_sustained_active',
         'sm__pipe_fma_cycles_active.avg.pct_of_peak_sustained_active',
+        'sm__pipe_fmaheavy_cycles_active.avg.pct_of_peak_sustained_elapsed',
+        'sm__inst_executed_pipe_fmaheavy.avg.pct_of_peak_sustained_active',
+        'sm__inst_executed_pipe_uniform.avg.pct_of_peak_sustained_active',
+        'sm__inst_executed_pipe_tmem.avg.pct_of_peak_sustained_active',
+        'smsp__sass_inst_executed_op_tmem_ldt.sum', 'smsp__sass_inst_executed_op_tmem_stt.sum',
+        'smsp__inst_executed.sum',
         'launch__registers_per_thread', 'launch__grid_size', 'launch__block_size',
         'l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum', 'lts__t_sector_hit_rate.pct',
         'l1tex__t_sector_hit_rate.pct']
