@@ -85,6 +85,33 @@ __device__ __forceinline__ void gs_bfly(uint32_t &x, uint32_t &y, uint32_t w, ui
 }
 
 
+// The same butterfly for moduli below 2^29, where 8q fits a word: sums may stay in [0, 4q).
+// bin is the compile-time bound of both inputs in units of q (1: canonical, 2, 4).  A sum of
+// two values below 2q is left alone (it is below 4q), a sum of two values below 4q takes one
+// conditional subtraction of 4q; the difference is offset by 2q or 4q so it stays positive
+// and below 8q <= 2^32, which is all Shoup's estimate needs for a result in [0, 2q).  After
+// the second stage of a round only the butterflies whose inputs were sums of the previous
+// stage reduce at all -- half of them -- which takes 144 of the kernel's 416 VIADDMNMX away.
+// The final values are canonicalised as before, so the output is unchanged bit for bit.
+// (bin folds to a constant once the stage loops are unrolled)
+__device__ __forceinline__ void gs_bfly_l4(const int bin, uint32_t &x, uint32_t &y, uint32_t w,
+                                           uint32_t wp, uint32_t q, uint32_t two_q, uint32_t four_q,
+                                           uint32_t zero) {
+    uint32_t s = x + y + zero;
+    uint32_t d = x - y + (bin == 4 ? four_q : two_q);
+    if (bin == 4) s = min(s - four_q, s);
+    uint32_t h = __umulhi(d, wp);
+    x = s;
+    y = d * w - h * q;
+}
+// input bound of the butterfly on registers (i0, i0 + 2^S) in stage S of a round whose inputs
+// are bounded by BIN0 (1 or 2: nothing reduces before stage 2; 4: the round starts reduced)
+__host__ __device__ constexpr int l4_bound(int S, int i0, int BIN0) {
+    if (S == 0) return BIN0;
+    if (S == 1 && BIN0 == 1) return 2;   // sums of canonical values are below 2q like the products
+    return ((i0 >> (S - 1)) & 1) ? 2 : 4;
+}
+
 // Lazy Harvey Cooley-Tukey butterfly on values in [0, 4q): x is brought to [0, 2q),
 // v = y*w in [0, 2q) by Shoup; outputs x+v and x-v+2q, both in [0, 4q).  4q < 2^32.
 template <bool REDUCE_X>

@@ -62,12 +62,26 @@ __device__ __forceinline__ void gs_bfly_final(uint32_t &x, uint32_t &y, uint32_t
     y = min(r - q, r);
 }
 
+// last stage, 4q-lazy inputs bounded by bin * q
+__device__ __forceinline__ void gs_bfly_final_l4(const int bin, uint32_t &x, uint32_t &y, uint32_t w,
+                                                 uint32_t wp, uint32_t q, uint32_t two_q,
+                                                 uint32_t four_q, uint32_t zero) {
+    uint32_t s = x + y + zero;
+    uint32_t d = x - y + (bin == 4 ? four_q : two_q);
+    if (bin == 4) s = min(s - four_q, s);
+    s = min(s - two_q, s);
+    uint32_t h = __umulhi(d, wp);
+    uint32_t r = d * w - h * q;
+    x = min(s - q, s);
+    y = min(r - q, r);
+}
+
 // round 1, stage S (stride 2^S inside the thread's 64 contiguous coefficients).
 // Twiddle of local block b: table[(2048 >> S) + j*(32 >> S) + b]; the (w, w')
 // pairs of one thread sit in shared memory as uint4 slots [slot][thread].
-template <int S>
+template <int S, bool L4>
 __device__ __forceinline__ void round1_stage(uint32_t (&v)[64], uint32_t tw_addr, uint32_t q,
-                                             uint32_t two_q, uint32_t zero) {
+                                             uint32_t two_q, uint32_t four_q, uint32_t zero) {
     constexpr int kBlocks = 32 >> S;                       // distinct twiddles
     constexpr int kSlot0 = 32 - (kBlocks >= 2 ? kBlocks : 1);  // 0,16,24,28,30,31
     constexpr int kStride = 1 << S;
@@ -77,22 +91,30 @@ __device__ __forceinline__ void round1_stage(uint32_t (&v)[64], uint32_t tw_addr
 #pragma unroll
         for (int e = 0; e < kStride; e++) {
             int i0 = b * 2 * kStride + e;
-            gs_bfly<(S > 0)>(v[i0], v[i0 + kStride], t.x, t.y, q, two_q, zero);
+            if (L4) {
+                gs_bfly_l4(l4_bound(S, e, 1), v[i0], v[i0 + kStride], t.x, t.y, q, two_q, four_q, zero);
+            } else {
+                gs_bfly<(S > 0)>(v[i0], v[i0 + kStride], t.x, t.y, q, two_q, zero);
+            }
         }
         if (kBlocks >= 2) {
 #pragma unroll
             for (int e = 0; e < kStride; e++) {
                 int i0 = (b + 1) * 2 * kStride + e;
-                gs_bfly<(S > 0)>(v[i0], v[i0 + kStride], t.z, t.w, q, two_q, zero);
+                if (L4) {
+                    gs_bfly_l4(l4_bound(S, e, 1), v[i0], v[i0 + kStride], t.z, t.w, q, two_q, four_q, zero);
+                } else {
+                    gs_bfly<(S > 0)>(v[i0], v[i0 + kStride], t.z, t.w, q, two_q, zero);
+                }
             }
         }
     }
 }
 
 // round 2, stage K (pairs registers i and i + 2^K); twiddle table[(32 >> K) + (i >> (K+1))]
-template <int K>
+template <int K, bool L4>
 __device__ __forceinline__ void round2_stage(uint32_t (&v)[64], const UniformTw &u, uint32_t q,
-                                             uint32_t two_q, uint32_t zero) {
+                                             uint32_t two_q, uint32_t four_q, uint32_t zero) {
     constexpr int kStride = 1 << K;
 #pragma unroll
     for (int b = 0; b < (32 >> K); b++) {
@@ -100,7 +122,14 @@ __device__ __forceinline__ void round2_stage(uint32_t (&v)[64], const UniformTw 
 #pragma unroll
         for (int e = 0; e < kStride; e++) {
             int i0 = b * 2 * kStride + e;
-            if (K == 5) {
+            if (L4) {
+                // round 2 starts from whatever round 1 left (at most 4q, thread dependent)
+                if (K == 5) {
+                    gs_bfly_final_l4(l4_bound(K, e, 4), v[i0], v[i0 + kStride], w, wp, q, two_q, four_q, zero);
+                } else {
+                    gs_bfly_l4(l4_bound(K, e, 4), v[i0], v[i0 + kStride], w, wp, q, two_q, four_q, zero);
+                }
+            } else if (K == 5) {
                 gs_bfly_final(v[i0], v[i0 + kStride], w, wp, q, two_q, zero);
             } else {
                 gs_bfly<true>(v[i0], v[i0 + kStride], w, wp, q, two_q, zero);
@@ -115,6 +144,7 @@ struct FusedParams {
     uint64_t batch;
     uint32_t q;
     uint32_t zero;        // always 0 (see gs_bfly)
+    uint32_t four_q;      // 4q as an opaque value (computed in the kernel it is folded into LEA + VIMNMX)
     uint32_t permute;     // ans_order on store (reference src/test.cpp:69-71,212-219)
     uint32_t scale;       // SCALE: every output times this constant (Shoup pair) -- the
     uint32_t scale_shoup; // N^-1 of an inverse transform, fused into the store
@@ -130,7 +160,7 @@ struct FusedParams {
 // (Measured and kept out of this kernel: round-1 twiddles in tensor memory instead of the
 // 32 KiB shared-memory table, 0.471 against 0.462 ms; CTA-wide instead of team barriers,
 // 0.516 ms.)
-template <bool PERMUTE, bool SCALE = false, bool IN_BR = false, bool OUT_BR = false>
+template <bool PERMUTE, bool SCALE = false, bool IN_BR = false, bool OUT_BR = false, bool L4 = false>
 __global__ void __launch_bounds__(kF_Threads, 1)
 fused_gs4096_kernel(const __grid_constant__ CUtensorMap map_lo,
                     const __grid_constant__ CUtensorMap map_hi,
@@ -148,28 +178,33 @@ fused_gs4096_kernel(const __grid_constant__ CUtensorMap map_lo,
     // registers instead of taking a third vector-register read port in every IADD3
     const int team = __shfl_sync(0xffffffffu, tid >> 6, 0);
     const int j = tid & 63;
-    const uint32_t q = prm.q, two_q = 2u * prm.q, zero = prm.zero;
+    const uint32_t q = prm.q, two_q = 2u * prm.q, four_q = prm.four_q, zero = prm.zero;
 
+    // Polynomial p goes to team (p / gridDim.x) % kF_Teams of CTA p % gridDim.x: consecutive
+    // polynomials land on different SMs, so a batch that is not a multiple of gridDim.x * kF_Teams
+    // ends with every SM running a few teams instead of a few SMs running all eight.
+    const uint32_t buf = data_base + team * kF_PolyBytes;
+    const uint32_t bar = bar_base + team * 8;
+    const uint64_t stride = (uint64_t) gridDim.x * kF_Teams;
+    uint64_t poly = (uint64_t) team * gridDim.x + blockIdx.x;
+    uint32_t parity = 0;
+
+    // the team's first load is in flight while the CTA stages the twiddles
+    if (j == 0) {
+        mbar_init(bar, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        if (poly < prm.batch) {
+            mbar_expect_tx(bar, kF_PolyBytes);
+            tma_load_3d(buf, &map_lo, bar, 0, 0, (int) poly);
+            tma_load_3d(buf + kF_PolyBytes / 2, &map_hi, bar, 0, 0, (int) poly);
+        }
+    }
     // stage the round-1 twiddles (kernel-private order, prepared at plan time)
     for (int i = tid; i < kF_TwSlots * kF_Team; i += kF_Threads) {
         uint4 t = __ldg(prm.tw_r1 + i);
         sts128(tw_base + i * 16, t.x, t.y, t.z, t.w);
     }
-    if (tid < kF_Teams) mbar_init(bar_base + tid * 8, 1);
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     __syncthreads();
-
-    const uint32_t buf = data_base + team * kF_PolyBytes;
-    const uint32_t bar = bar_base + team * 8;
-    const uint64_t stride = (uint64_t) gridDim.x * kF_Teams;
-    uint64_t poly = (uint64_t) blockIdx.x * kF_Teams + team;
-    uint32_t parity = 0;
-
-    if (j == 0 && poly < prm.batch) {
-        mbar_expect_tx(bar, kF_PolyBytes);
-        tma_load_3d(buf, &map_lo, bar, 0, 0, (int) poly);
-        tma_load_3d(buf + kF_PolyBytes / 2, &map_hi, bar, 0, 0, (int) poly);
-    }
 
     // shared-memory addresses.  Buffer layout (as TMA writes it): two halves of
     // [64 rows][32 words], row r / half h holds a[64r + 32h .. +31]; the 16-byte
@@ -206,12 +241,12 @@ fused_gs4096_kernel(const __grid_constant__ CUtensorMap map_lo,
                 v[4 * c + 3] = t.w;
             }
         }
-        round1_stage<0>(v, tw_addr, q, two_q, zero);
-        round1_stage<1>(v, tw_addr, q, two_q, zero);
-        round1_stage<2>(v, tw_addr, q, two_q, zero);
-        round1_stage<3>(v, tw_addr, q, two_q, zero);
-        round1_stage<4>(v, tw_addr, q, two_q, zero);
-        round1_stage<5>(v, tw_addr, q, two_q, zero);
+        round1_stage<0, L4>(v, tw_addr, q, two_q, four_q, zero);
+        round1_stage<1, L4>(v, tw_addr, q, two_q, four_q, zero);
+        round1_stage<2, L4>(v, tw_addr, q, two_q, four_q, zero);
+        round1_stage<3, L4>(v, tw_addr, q, two_q, four_q, zero);
+        round1_stage<4, L4>(v, tw_addr, q, two_q, four_q, zero);
+        round1_stage<5, L4>(v, tw_addr, q, two_q, four_q, zero);
 
         // ---- exchange through the same buffer (row write, column read)
 #pragma unroll
@@ -236,12 +271,12 @@ fused_gs4096_kernel(const __grid_constant__ CUtensorMap map_lo,
         }
 
         // ---- round 2: stages 6..11, uniform twiddles from the constant bank
-        round2_stage<0>(v, uni, q, two_q, zero);
-        round2_stage<1>(v, uni, q, two_q, zero);
-        round2_stage<2>(v, uni, q, two_q, zero);
-        round2_stage<3>(v, uni, q, two_q, zero);
-        round2_stage<4>(v, uni, q, two_q, zero);
-        round2_stage<5>(v, uni, q, two_q, zero);
+        round2_stage<0, L4>(v, uni, q, two_q, four_q, zero);
+        round2_stage<1, L4>(v, uni, q, two_q, four_q, zero);
+        round2_stage<2, L4>(v, uni, q, two_q, four_q, zero);
+        round2_stage<3, L4>(v, uni, q, two_q, four_q, zero);
+        round2_stage<4, L4>(v, uni, q, two_q, four_q, zero);
+        round2_stage<5, L4>(v, uni, q, two_q, four_q, zero);
 
         // ---- store: register i is coefficient j + 64 i; a warp writes 128 B rows
         if (OUT_BR) {
@@ -349,6 +384,8 @@ int fused_prepare(nttb200_plan *p) {
                                       cudaFuncAttributeMaxDynamicSharedMemorySize, kF_SmemBytes));
     NTTB200_CUDA(cudaFuncSetAttribute(fused_gs4096_kernel<true>,
                                       cudaFuncAttributeMaxDynamicSharedMemorySize, kF_SmemBytes));
+    NTTB200_CUDA(cudaFuncSetAttribute(fused_gs4096_kernel<false, false, false, false, true>,
+                                      cudaFuncAttributeMaxDynamicSharedMemorySize, kF_SmemBytes));
     NTTB200_CUDA(cudaFuncSetAttribute(fused_gs4096_kernel<false, true>,
                                       cudaFuncAttributeMaxDynamicSharedMemorySize, kF_SmemBytes));
     NTTB200_CUDA(cudaFuncSetAttribute(fused_gs4096_kernel<false, false, true, false>,
@@ -368,6 +405,11 @@ void fused_release(nttb200_plan *p) {
 static int launch_fused_impl(nttb200_plan *p, const int32_t *d_in, int32_t *d_out, size_t batch,
                              bool permute_out, bool scaled, cudaStream_t st, bool in_br = false,
                              bool out_br = false);
+
+static bool l4_enabled() {   // NTTB200_NO_L4=1: A/B switch for measurements
+    static const bool on = getenv("NTTB200_NO_L4") == nullptr;
+    return on;
+}
 
 int launch_fused_gs(nttb200_plan *p, const int32_t *d_in, int32_t *d_out, size_t batch,
                     bool permute_out, cudaStream_t st) {
@@ -406,6 +448,7 @@ static int launch_fused_impl(nttb200_plan *p, const int32_t *d_in, int32_t *d_ou
     prm.batch = batch;
     prm.q = p->q;
     prm.zero = 0;
+    prm.four_q = 4u * p->q;   // only used when 8q fits a word
     prm.permute = permute_out;
     prm.scale = prm.scale_shoup = 0;
     if (scaled) {
@@ -413,8 +456,7 @@ static int launch_fused_impl(nttb200_plan *p, const int32_t *d_in, int32_t *d_ou
         prm.scale = (uint32_t) sc;
         prm.scale_shoup = (uint32_t) ((sc << 32) / p->q);
     }
-    uint64_t ctas = (batch + kF_Teams - 1) / kF_Teams;
-    int grid = (int) (ctas < (uint64_t) p->sm_count ? ctas : (uint64_t) p->sm_count);
+    int grid = (int) (batch < (uint64_t) p->sm_count ? batch : (uint64_t) p->sm_count);
     if (scaled) {
         fused_gs4096_kernel<false, true><<<grid, kF_Threads, kF_SmemBytes, st>>>(map_lo, map_hi,
                                                                                  p->uni_gs, prm);
@@ -429,6 +471,10 @@ static int launch_fused_impl(nttb200_plan *p, const int32_t *d_in, int32_t *d_ou
             map_lo, map_hi, p->uni_gs, prm);
     } else if (out_br) {
         fused_gs4096_kernel<false, false, false, true><<<grid, kF_Threads, kF_SmemBytes, st>>>(
+            map_lo, map_hi, p->uni_gs, prm);
+    } else if (p->q < (1u << 29) && l4_enabled()) {
+        // 8q fits a word: the 4q-lazy butterflies (fused_common.cuh, gs_bfly_l4)
+        fused_gs4096_kernel<false, false, false, false, true><<<grid, kF_Threads, kF_SmemBytes, st>>>(
             map_lo, map_hi, p->uni_gs, prm);
     } else {
         fused_gs4096_kernel<false><<<grid, kF_Threads, kF_SmemBytes, st>>>(map_lo, map_hi,
