@@ -125,6 +125,35 @@ __device__ __forceinline__ void ct_bfly(uint32_t &x, uint32_t &y, uint32_t w, ui
 }
 
 
+// The forward butterfly for moduli below 2^29: x may grow to 8q.  bin = bound of x in units
+// of q; x + v and x - v + 2q are below (bin + 2) q, so x only needs its conditional
+// subtraction (of 4q) when bin > 6 -- every other stage after the first three -- and y can be
+// any word (Shoup's estimate holds for every 32-bit operand).
+__host__ __device__ constexpr int ct_l4_out(int bin) { return (bin > 6 ? 4 : bin) + 2; }
+__host__ __device__ constexpr int ct_l4_out_n(int bin, int stages) {
+    for (int k = 0; k < stages; k++) bin = ct_l4_out(bin);
+    return bin;
+}
+// The last stage of a transform (bin < 0, bound -bin) brings x below 2q instead, so that both
+// outputs are below 4q and canonicalise with two conditional subtractions.
+__device__ __forceinline__ void ct_bfly_l4(const int bin, uint32_t &x, uint32_t &y, uint32_t w,
+                                           uint32_t wp, uint32_t q, uint32_t two_q, uint32_t four_q,
+                                           uint32_t zero) {
+    uint32_t xr = (bin > 6 || bin < -4) ? min(x - four_q, x) : x;
+    if (bin < -2) xr = min(xr - two_q, xr);
+    uint32_t h = __umulhi(y, wp);
+    uint32_t v = y * w - h * q;
+    x = xr + v + zero;
+    y = xr - v + two_q;
+}
+// value below bin * q -> canonical
+__device__ __forceinline__ uint32_t canon_l4(const int bin, uint32_t r, uint32_t q, uint32_t two_q,
+                                             uint32_t four_q) {
+    if (bin > 4) r = min(r - four_q, r);
+    if (bin > 2) r = min(r - two_q, r);
+    return min(r - q, r);
+}
+
 __device__ __forceinline__ void tma_store_3d(const CUtensorMap *map, uint32_t src, int c0, int c1,
                                              int c2) {
     asm volatile(
@@ -247,6 +276,34 @@ __device__ __forceinline__ void ct_blocks(uint32_t (&v)[64], const uint32_t *t, 
     }
 }
 
+template <int S, int B0, int NB, int BIN0>
+__device__ __forceinline__ void gs_blocks_l4(uint32_t (&v)[64], const uint32_t *t, uint32_t q,
+                                             uint32_t two_q, uint32_t four_q, uint32_t zero) {
+    constexpr int kStride = 1 << S;
+#pragma unroll
+    for (int k = 0; k < NB; k++) {
+#pragma unroll
+        for (int e = 0; e < kStride; e++) {
+            const int i0 = (B0 + k) * 2 * kStride + e;
+            gs_bfly_l4(l4_bound(S, e, BIN0), v[i0], v[i0 + kStride], t[2 * k], t[2 * k + 1], q, two_q,
+                       four_q, zero);
+        }
+    }
+}
+template <int S, int B0, int NB, int BIN>
+__device__ __forceinline__ void ct_blocks_l4(uint32_t (&v)[64], const uint32_t *t, uint32_t q,
+                                             uint32_t two_q, uint32_t four_q, uint32_t zero) {
+    constexpr int kStride = 1 << S;
+#pragma unroll
+    for (int k = 0; k < NB; k++) {
+#pragma unroll
+        for (int e = 0; e < kStride; e++) {
+            const int i0 = (B0 + k) * 2 * kStride + e;
+            ct_bfly_l4(BIN, v[i0], v[i0 + kStride], t[2 * k], t[2 * k + 1], q, two_q, four_q, zero);
+        }
+    }
+}
+
 // GS stages 0..5 on the thread's 64 registers, private twiddles from the thread's
 // 128-word TMEM table at `taddr` (slot layout of fused_prepare / tile_table_kernel:
 // slots 0-15 stage 0, 16-23 stage 1, 24-27 stage 2, 28-29 stage 3, 30 stage 4, 31 stage 5;
@@ -315,6 +372,75 @@ __device__ __forceinline__ void ct_round_tmem(uint32_t (&v)[64], uint32_t taddr,
     ct_blocks<0, 8, 8, true>(v, tb, q, two_q, zero);
     tmem_wait_ld16(ta);
     ct_blocks<0, 0, 8, true>(v, ta, q, two_q, zero);
+}
+
+// 4q-lazy forms of the two rounds above (q < 2^29).  GS: inputs bounded by BIN0 * q, outputs
+// below 4q (sums) / 2q (products).  CT: inputs below BIN0 * q, outputs below
+// ct_l4_out_n(BIN0, 6) * q -- or below 4q when the round is the LAST of the transform.
+template <int BIN0>
+__device__ __forceinline__ void gs_round_tmem_l4(uint32_t (&v)[64], uint32_t taddr, uint32_t q,
+                                                 uint32_t two_q, uint32_t four_q, uint32_t zero) {
+    uint32_t ta[16], tb[16];
+    tmem_ld16(taddr, ta);
+    tmem_wait_ld16(ta);
+    tmem_ld16(taddr + 16, tb);
+    gs_blocks_l4<0, 0, 8, BIN0>(v, ta, q, two_q, four_q, zero);
+    tmem_wait_ld16(tb);
+    tmem_ld16(taddr + 32, ta);
+    gs_blocks_l4<0, 8, 8, BIN0>(v, tb, q, two_q, four_q, zero);
+    tmem_wait_ld16(ta);
+    tmem_ld16(taddr + 48, tb);
+    gs_blocks_l4<0, 16, 8, BIN0>(v, ta, q, two_q, four_q, zero);
+    tmem_wait_ld16(tb);
+    tmem_ld16(taddr + 64, ta);
+    gs_blocks_l4<0, 24, 8, BIN0>(v, tb, q, two_q, four_q, zero);
+    tmem_wait_ld16(ta);
+    tmem_ld16(taddr + 80, tb);
+    gs_blocks_l4<1, 0, 8, BIN0>(v, ta, q, two_q, four_q, zero);
+    tmem_wait_ld16(tb);
+    tmem_ld16(taddr + 96, ta);
+    gs_blocks_l4<1, 8, 8, BIN0>(v, tb, q, two_q, four_q, zero);
+    tmem_wait_ld16(ta);
+    tmem_ld16(taddr + 112, tb);
+    gs_blocks_l4<2, 0, 8, BIN0>(v, ta, q, two_q, four_q, zero);
+    tmem_wait_ld16(tb);
+    gs_blocks_l4<3, 0, 4, BIN0>(v, tb, q, two_q, four_q, zero);
+    gs_blocks_l4<4, 0, 2, BIN0>(v, tb + 8, q, two_q, four_q, zero);
+    gs_blocks_l4<5, 0, 1, BIN0>(v, tb + 12, q, two_q, four_q, zero);
+}
+template <int BIN0, bool LAST = false>
+__device__ __forceinline__ void ct_round_tmem_l4(uint32_t (&v)[64], uint32_t taddr, uint32_t q,
+                                                 uint32_t two_q, uint32_t four_q, uint32_t zero) {
+    constexpr int B5 = BIN0, B4 = ct_l4_out(B5), B3 = ct_l4_out(B4), B2 = ct_l4_out(B3),
+                  B1 = ct_l4_out(B2), B0 = ct_l4_out(B1);
+    uint32_t ta[16], tb[16];
+    tmem_ld16(taddr + 112, tb);
+    tmem_wait_ld16(tb);
+    tmem_ld16(taddr + 96, ta);
+    ct_blocks_l4<5, 0, 1, B5>(v, tb + 12, q, two_q, four_q, zero);
+    ct_blocks_l4<4, 0, 2, B4>(v, tb + 8, q, two_q, four_q, zero);
+    ct_blocks_l4<3, 0, 4, B3>(v, tb, q, two_q, four_q, zero);
+    tmem_wait_ld16(ta);
+    tmem_ld16(taddr + 80, tb);
+    ct_blocks_l4<2, 0, 8, B2>(v, ta, q, two_q, four_q, zero);
+    tmem_wait_ld16(tb);
+    tmem_ld16(taddr + 64, ta);
+    ct_blocks_l4<1, 8, 8, B1>(v, tb, q, two_q, four_q, zero);
+    tmem_wait_ld16(ta);
+    tmem_ld16(taddr + 48, tb);
+    ct_blocks_l4<1, 0, 8, B1>(v, ta, q, two_q, four_q, zero);
+    tmem_wait_ld16(tb);
+    tmem_ld16(taddr + 32, ta);
+    constexpr int BL = LAST ? -B0 : B0;
+    ct_blocks_l4<0, 24, 8, BL>(v, tb, q, two_q, four_q, zero);
+    tmem_wait_ld16(ta);
+    tmem_ld16(taddr + 16, tb);
+    ct_blocks_l4<0, 16, 8, BL>(v, ta, q, two_q, four_q, zero);
+    tmem_wait_ld16(tb);
+    tmem_ld16(taddr, ta);
+    ct_blocks_l4<0, 8, 8, BL>(v, tb, q, two_q, four_q, zero);
+    tmem_wait_ld16(ta);
+    ct_blocks_l4<0, 0, 8, BL>(v, ta, q, two_q, four_q, zero);
 }
 
 }  // namespace nttb200

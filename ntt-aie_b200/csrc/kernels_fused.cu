@@ -406,7 +406,7 @@ static int launch_fused_impl(nttb200_plan *p, const int32_t *d_in, int32_t *d_ou
                              bool permute_out, bool scaled, cudaStream_t st, bool in_br = false,
                              bool out_br = false);
 
-static bool l4_enabled() {   // NTTB200_NO_L4=1: A/B switch for measurements
+bool l4_enabled() {
     static const bool on = getenv("NTTB200_NO_L4") == nullptr;
     return on;
 }
@@ -472,7 +472,7 @@ static int launch_fused_impl(nttb200_plan *p, const int32_t *d_in, int32_t *d_ou
     } else if (out_br) {
         fused_gs4096_kernel<false, false, false, true><<<grid, kF_Threads, kF_SmemBytes, st>>>(
             map_lo, map_hi, p->uni_gs, prm);
-    } else if (p->q < (1u << 29) && l4_enabled()) {
+    } else if (use_l4(p)) {
         // 8q fits a word: the 4q-lazy butterflies (fused_common.cuh, gs_bfly_l4)
         fused_gs4096_kernel<false, false, false, false, true><<<grid, kF_Threads, kF_SmemBytes, st>>>(
             map_lo, map_hi, p->uni_gs, prm);

@@ -561,7 +561,7 @@ constexpr int kD_Teams = 6;
 constexpr int kD_Threads = kD_Teams * kF_Team;
 constexpr int kD_SmemBytes = kD_Teams * 2 * kF_PolyBytes + kM_TwTile * 16 + 128 + 1024;
 
-template <bool MULT>
+template <bool MULT, bool L4 = false>
 __global__ void __launch_bounds__(kD_Threads, 1)
 tile_ct_db_kernel(const __grid_constant__ CUtensorMap map_lo, const __grid_constant__ CUtensorMap map_hi,
                   const __grid_constant__ CUtensorMap out_lo, const __grid_constant__ CUtensorMap out_hi,
@@ -574,7 +574,7 @@ tile_ct_db_kernel(const __grid_constant__ CUtensorMap map_lo, const __grid_const
     const int tid = threadIdx.x;
     const int team = __shfl_sync(0xffffffffu, tid >> 6, 0);
     const int j = tid & 63;
-    const uint32_t q = prm.q, two_q = 2u * prm.q, zero = prm.zero;
+    const uint32_t q = prm.q, two_q = 2u * prm.q, four_q = prm.four_q, zero = prm.zero;
 
     for (int i = tid; i < kM_TwTile; i += kD_Threads) {
         uint4 x = __ldg(prm.tw_tile + i);
@@ -630,12 +630,17 @@ tile_ct_db_kernel(const __grid_constant__ CUtensorMap map_lo, const __grid_const
             v[i] = lds32(r2_col + i * 128 + (r2_chunk ^ ((i & 7) << 4)));
         }
         // stages 11..6: twiddles table[1..63] from the constant bank
-        ct_stage_uniform<5, false>(v, uni, q, two_q, zero);
-        ct_stage_uniform<4, true>(v, uni, q, two_q, zero);
-        ct_stage_uniform<3, true>(v, uni, q, two_q, zero);
-        ct_stage_uniform<2, true>(v, uni, q, two_q, zero);
-        ct_stage_uniform<1, true>(v, uni, q, two_q, zero);
-        ct_stage_uniform<0, true>(v, uni, q, two_q, zero);
+        constexpr int kBCol = ct_l4_out_n(1, 6), kBRow = ct_l4_out_n(kBCol, 6);   // L4 bounds
+        if (L4) {
+            ct_round_uniform_l4<1>(v, uni, q, two_q, four_q, zero);
+        } else {
+            ct_stage_uniform<5, false>(v, uni, q, two_q, zero);
+            ct_stage_uniform<4, true>(v, uni, q, two_q, zero);
+            ct_stage_uniform<3, true>(v, uni, q, two_q, zero);
+            ct_stage_uniform<2, true>(v, uni, q, two_q, zero);
+            ct_stage_uniform<1, true>(v, uni, q, two_q, zero);
+            ct_stage_uniform<0, true>(v, uni, q, two_q, zero);
+        }
 #pragma unroll
         for (int i = 0; i < 64; i++) {
             asm volatile("st.shared.u32 [%0], %1;" ::"r"(r2_col + i * 128 + (r2_chunk ^ ((i & 7) << 4))),
@@ -660,7 +665,11 @@ tile_ct_db_kernel(const __grid_constant__ CUtensorMap map_lo, const __grid_const
                 tma_load_3d(buf + kF_PolyBytes / 2, &mul_hi, bar, 0, 0, (int) tile);
             }
         }
-        ct_round<true>(v, TwShared{tws + j * 16}, q, two_q, zero);
+        if (L4) {
+            ct_round_l4<kBCol>(v, TwShared{tws + j * 16}, q, two_q, four_q, zero);
+        } else {
+            ct_round<true>(v, TwShared{tws + j * 16}, q, two_q, zero);
+        }
         if (MULT) {
             if (cur == 0) {
                 mbar_wait(bar, parity0);
@@ -681,13 +690,18 @@ tile_ct_db_kernel(const __grid_constant__ CUtensorMap map_lo, const __grid_const
 #pragma unroll
             for (int e = 0; e < 4; e++) {
                 uint32_t r = v[4 * c + e];
-                r = min(r - two_q, r);
                 if (MULT) {
+                    // any word times a canonical value is below 2^32 q: no reduction first
                     uint64_t prod = (uint64_t) r * ob[e];
                     uint32_t m = (uint32_t) prod * prm.qinv;
                     r = (uint32_t) (prod >> 32) - __umulhi(m, q) + q;
+                    o[e] = min(r - q, r);
+                } else if (L4) {
+                    o[e] = canon_l4(kBRow, r, q, two_q, four_q);
+                } else {
+                    r = min(r - two_q, r);
+                    o[e] = min(r - q, r);
                 }
-                o[e] = min(r - q, r);
             }
             sts128(r1_row + (c >> 3) * (kF_PolyBytes / 2) + (((c & 7) << 4) ^ r1_xor), o[0], o[1],
                    o[2], o[3]);
@@ -987,6 +1001,8 @@ int multi_set_attrs() {
     NTTB200_CUDA(cudaFuncSetAttribute(tile_ct_kernel<false, true, true>, attr, kM_SmemBytesTw));
     NTTB200_CUDA(cudaFuncSetAttribute(tile_ct_db_kernel<false>, attr, kD_SmemBytes));
     NTTB200_CUDA(cudaFuncSetAttribute(tile_ct_db_kernel<true>, attr, kD_SmemBytes));
+    NTTB200_CUDA(cudaFuncSetAttribute(tile_ct_db_kernel<false, true>, attr, kD_SmemBytes));
+    NTTB200_CUDA(cudaFuncSetAttribute(tile_ct_db_kernel<true, true>, attr, kD_SmemBytes));
     NTTB200_CUDA(cudaFuncSetAttribute(poly_ct_kernel<1>, attr, kM_SmemBytes));
     NTTB200_CUDA(cudaFuncSetAttribute(poly_ct_kernel<2>, attr, kM_SmemBytes));
     NTTB200_CUDA(cudaFuncSetAttribute(poly_ct_kernel<3>, attr, kM_SmemBytes));
@@ -1098,6 +1114,7 @@ static TileParams tile_params(nttb200_plan *p, int32_t *d_out, size_t batch) {
     tp.qinv = 0;
     tp.scale = 0;
     tp.scale_shoup = 0;
+    tp.four_q = 4u * p->q;
     return tp;
 }
 
@@ -1413,9 +1430,20 @@ int launch_multi_ct_mul(nttb200_plan *p, const int32_t *d_in, const int32_t *d_m
     if (tp.chunks == 1 && use_db && p->d_tw_r1) {  // d_tw_r1 set <=> uni_gs holds table[1..63]
         uint64_t ctas = (tiles + kD_Teams - 1) / kD_Teams;
         int grid = (int) (ctas < (uint64_t) p->sm_count ? ctas : (uint64_t) p->sm_count);
-        if (d_mul) {
+        // measured: the 4q-lazy schedule is 4.7 % SLOWER in this kernel (0.542 against 0.518 ms per
+        // 65,536 tiles; its conditional subtractions bunch up at the end of the tile while the six
+        // teams run in lockstep), so it stays opt-in (NTTB200_CT_L4=1)
+        static const bool ct_l4 = getenv("NTTB200_CT_L4") != nullptr;
+        const bool l4 = ct_l4 && use_l4(p);
+        if (d_mul && l4) {
+            tile_ct_db_kernel<true, true><<<grid, kD_Threads, kD_SmemBytes, st>>>(
+                in_lo, in_hi, out_lo, out_hi, mul_lo, mul_hi, p->uni_gs, tp);
+        } else if (d_mul) {
             tile_ct_db_kernel<true><<<grid, kD_Threads, kD_SmemBytes, st>>>(in_lo, in_hi, out_lo, out_hi,
                                                                            mul_lo, mul_hi, p->uni_gs, tp);
+        } else if (l4) {
+            tile_ct_db_kernel<false, true><<<grid, kD_Threads, kD_SmemBytes, st>>>(
+                in_lo, in_hi, out_lo, out_hi, in_lo, in_hi, p->uni_gs, tp);
         } else {
             tile_ct_db_kernel<false><<<grid, kD_Threads, kD_SmemBytes, st>>>(in_lo, in_hi, out_lo, out_hi,
                                                                             in_lo, in_hi, p->uni_gs, tp);
@@ -1463,6 +1491,7 @@ int rns_launch(int sm_count, int kind, const uint4 *d_tw_tile, const uint4 *h_po
     tp.q = 0;
     tp.zero = 0;
     tp.qinv = tp.scale = tp.scale_shoup = 0;
+    tp.four_q = 0;   // RNS primes sit just below 2^30: classic butterflies
     uint64_t ctas = (tiles + kM_Teams - 1) / kM_Teams;
     int grid = (int) (ctas < (uint64_t) sm_count ? ctas : (uint64_t) sm_count);
     CUtensorMap a_lo, a_hi, b_lo, b_hi;

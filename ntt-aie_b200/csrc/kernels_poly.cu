@@ -62,7 +62,7 @@ __device__ __forceinline__ uint32_t poly_prologue(const uint4 *tw_tile, uint32_t
     return lane_base;
 }
 
-template <int LOGG, bool DUAL>
+template <int LOGG, bool DUAL, bool L4>
 __global__ void __launch_bounds__(kM_Threads, 1)
 polyt_gs_kernel(const __grid_constant__ CUtensorMap map_lo, const __grid_constant__ CUtensorMap map_hi,
                 const __grid_constant__ CUtensorMap map_b_lo,
@@ -79,7 +79,7 @@ polyt_gs_kernel(const __grid_constant__ CUtensorMap map_lo, const __grid_constan
     const int team = warp >> 1;
     const int j = tid & 63;
     const int grp = team >> LOGG, t = team & (G - 1);
-    const uint32_t q = prm.q, two_q = 2u * prm.q, zero = prm.zero;
+    const uint32_t q = prm.q, two_q = 2u * prm.q, four_q = prm.four_q, zero = prm.zero;
 
     uint32_t tmem_base;
     const uint32_t lane_base = poly_prologue<G>(prm.tw_tile, bar_base, tid, warp, j, tmem_base);
@@ -141,7 +141,11 @@ polyt_gs_kernel(const __grid_constant__ CUtensorMap map_lo, const __grid_constan
             }
         }
         // ---- round 1: stages 0..5, private pairs from tensor memory
-        gs_round_tmem<DUAL>(v, tw1, q, two_q, zero);
+        if (L4) {
+            gs_round_tmem_l4<(DUAL ? 2 : 1)>(v, tw1, q, two_q, four_q, zero);
+        } else {
+            gs_round_tmem<DUAL>(v, tw1, q, two_q, zero);
+        }
 #pragma unroll
         for (int c = 0; c < 16; c++) {
             sts128(r1_row + (c >> 3) * (kF_PolyBytes / 2) + (((c & 7) << 4) ^ r1_xor), v[4 * c],
@@ -154,7 +158,11 @@ polyt_gs_kernel(const __grid_constant__ CUtensorMap map_lo, const __grid_constan
         }
         team_sync(team);
         // ---- round 2: stages 6..11, the position's 63 pairs from shared memory
-        gs_round<true>(v, tw2, q, two_q, zero);
+        if (L4) {
+            gs_round_l4<4>(v, tw2, q, two_q, four_q, zero);
+        } else {
+            gs_round<true>(v, tw2, q, two_q, zero);
+        }
 
         // ---- round 3: register i is a[t*4096 + j + 64 i].  Park it at [i][j] of this
         // team's buffer, then collect rows t*kSlice .. +kSlice-1 of ALL G tiles.
@@ -193,8 +201,13 @@ polyt_gs_kernel(const __grid_constant__ CUtensorMap map_lo, const __grid_constan
                     const int t0 = (b2 << (m + 1)) + e;
 #pragma unroll
                     for (int ii = 0; ii < kSlice; ii++) {
-                        gs_bfly<true>(w[t0 * kSlice + ii], w[(t0 + (1 << m)) * kSlice + ii], cw, cwp, q,
-                                      two_q, zero);
+                        if (L4) {
+                            gs_bfly_l4(l4_bound(m, e, 4), w[t0 * kSlice + ii], w[(t0 + (1 << m)) * kSlice + ii],
+                                       cw, cwp, q, two_q, four_q, zero);
+                        } else {
+                            gs_bfly<true>(w[t0 * kSlice + ii], w[(t0 + (1 << m)) * kSlice + ii], cw, cwp, q,
+                                          two_q, zero);
+                        }
                     }
                 }
             }
@@ -205,7 +218,11 @@ polyt_gs_kernel(const __grid_constant__ CUtensorMap map_lo, const __grid_constan
 #pragma unroll
             for (int ii = 0; ii < kSlice; ii++) {
                 uint32_t r = w[tt * kSlice + ii];
-                if (DUAL) r = shoup_mul_lazy(r, prm.scale, prm.scale_shoup, q);
+                if (DUAL) {
+                    r = shoup_mul_lazy(r, prm.scale, prm.scale_shoup, q);   // any word in, [0, 2q) out
+                } else if (L4 && !((tt >> (LOGG - 1)) & 1)) {
+                    r = min(r - two_q, r);   // a sum of the last stage: below 4q
+                }
                 dst[tt * 4096 + ii * 64] = min(r - q, r);
             }
         }
@@ -218,7 +235,7 @@ polyt_gs_kernel(const __grid_constant__ CUtensorMap map_lo, const __grid_constan
 // Forward partner: the cross-tile stages come FIRST in the CT order (largest strides),
 // then every team finishes its own tile (columns, exchange, rows) and the rows leave
 // through a TMA store.
-template <int LOGG>
+template <int LOGG, bool L4>
 __global__ void __launch_bounds__(kM_Threads, 1)
 polyt_ct_kernel(const __grid_constant__ CUtensorMap map_lo, const __grid_constant__ CUtensorMap map_hi,
                 const __grid_constant__ CUtensorMap out_lo, const __grid_constant__ CUtensorMap out_hi,
@@ -234,7 +251,7 @@ polyt_ct_kernel(const __grid_constant__ CUtensorMap map_lo, const __grid_constan
     const int team = warp >> 1;
     const int j = tid & 63;
     const int grp = team >> LOGG, t = team & (G - 1);
-    const uint32_t q = prm.q, two_q = 2u * prm.q, zero = prm.zero;
+    const uint32_t q = prm.q, two_q = 2u * prm.q, four_q = prm.four_q, zero = prm.zero;
 
     uint32_t tmem_base;
     const uint32_t lane_base = poly_prologue<G>(prm.tw_tile, bar_base, tid, warp, j, tmem_base);
@@ -288,7 +305,10 @@ polyt_ct_kernel(const __grid_constant__ CUtensorMap map_lo, const __grid_constan
                     const int t0 = (b2 << (m + 1)) + e;
 #pragma unroll
                     for (int ii = 0; ii < kSlice; ii++) {
-                        if (mm == 0) {
+                        if (L4) {
+                            ct_bfly_l4(ct_l4_out_n(1, mm), v[t0 * kSlice + ii], v[(t0 + (1 << m)) * kSlice + ii],
+                                       cw, cwp, q, two_q, four_q, zero);
+                        } else if (mm == 0) {
                             ct_bfly<false>(v[t0 * kSlice + ii], v[(t0 + (1 << m)) * kSlice + ii], cw, cwp,
                                            q, two_q, zero);
                         } else {
@@ -316,7 +336,12 @@ polyt_ct_kernel(const __grid_constant__ CUtensorMap map_lo, const __grid_constan
         for (int i = 0; i < 64; i++) {
             v[i] = lds32(r2_col + i * 128 + (r2_chunk ^ ((i & 7) << 4)));
         }
-        ct_round<true>(v, tw2, q, two_q, zero);
+        constexpr int kB1 = ct_l4_out_n(1, LOGG), kB2 = ct_l4_out_n(kB1, 6), kB3 = ct_l4_out_n(kB2, 6);
+        if (L4) {
+            ct_round_l4<kB1>(v, tw2, q, two_q, four_q, zero);
+        } else {
+            ct_round<true>(v, tw2, q, two_q, zero);
+        }
 #pragma unroll
         for (int i = 0; i < 64; i++) {
             asm volatile("st.shared.u32 [%0], %1;" ::"r"(r2_col + i * 128 + (r2_chunk ^ ((i & 7) << 4))),
@@ -332,15 +357,23 @@ polyt_ct_kernel(const __grid_constant__ CUtensorMap map_lo, const __grid_constan
             v[4 * c + 2] = x.z;
             v[4 * c + 3] = x.w;
         }
-        ct_round_tmem<true>(v, tw1, q, two_q, zero);
+        if (L4) {
+            ct_round_tmem_l4<kB2>(v, tw1, q, two_q, four_q, zero);
+        } else {
+            ct_round_tmem<true>(v, tw1, q, two_q, zero);
+        }
 #pragma unroll
         for (int c = 0; c < 16; c++) {
             uint32_t o[4];
 #pragma unroll
             for (int e = 0; e < 4; e++) {
                 uint32_t r = v[4 * c + e];
-                r = min(r - two_q, r);
-                o[e] = min(r - q, r);
+                if (L4) {
+                    o[e] = canon_l4(kB3, r, q, two_q, four_q);
+                } else {
+                    r = min(r - two_q, r);
+                    o[e] = min(r - q, r);
+                }
             }
             sts128(r1_row + (c >> 3) * (kF_PolyBytes / 2) + (((c & 7) << 4) ^ r1_xor), o[0], o[1],
                    o[2], o[3]);
@@ -367,18 +400,23 @@ polyt_ct_kernel(const __grid_constant__ CUtensorMap map_lo, const __grid_constan
 // --------------------------------------------------------------------- host side
 int tile_maps(CUtensorMap *lo, CUtensorMap *hi, const int32_t *base, size_t tiles);  // kernels_fused.cu
 
-int polyt_prepare() {
+template <int LOGG>
+static int polyt_attrs() {
     const auto attr = cudaFuncAttributeMaxDynamicSharedMemorySize;
-    NTTB200_CUDA(cudaFuncSetAttribute(polyt_gs_kernel<1, false>, attr, kY_SmemBytes));
-    NTTB200_CUDA(cudaFuncSetAttribute(polyt_gs_kernel<2, false>, attr, kY_SmemBytes));
-    NTTB200_CUDA(cudaFuncSetAttribute(polyt_gs_kernel<3, false>, attr, kY_SmemBytes));
-    NTTB200_CUDA(cudaFuncSetAttribute(polyt_gs_kernel<1, true>, attr, kY_SmemBytes));
-    NTTB200_CUDA(cudaFuncSetAttribute(polyt_gs_kernel<2, true>, attr, kY_SmemBytes));
-    NTTB200_CUDA(cudaFuncSetAttribute(polyt_gs_kernel<3, true>, attr, kY_SmemBytes));
-    NTTB200_CUDA(cudaFuncSetAttribute(polyt_ct_kernel<1>, attr, kY_SmemBytes));
-    NTTB200_CUDA(cudaFuncSetAttribute(polyt_ct_kernel<2>, attr, kY_SmemBytes));
-    NTTB200_CUDA(cudaFuncSetAttribute(polyt_ct_kernel<3>, attr, kY_SmemBytes));
+    NTTB200_CUDA(cudaFuncSetAttribute(polyt_gs_kernel<LOGG, false, false>, attr, kY_SmemBytes));
+    NTTB200_CUDA(cudaFuncSetAttribute(polyt_gs_kernel<LOGG, true, false>, attr, kY_SmemBytes));
+    NTTB200_CUDA(cudaFuncSetAttribute(polyt_gs_kernel<LOGG, false, true>, attr, kY_SmemBytes));
+    NTTB200_CUDA(cudaFuncSetAttribute(polyt_gs_kernel<LOGG, true, true>, attr, kY_SmemBytes));
+    NTTB200_CUDA(cudaFuncSetAttribute(polyt_ct_kernel<LOGG, false>, attr, kY_SmemBytes));
+    NTTB200_CUDA(cudaFuncSetAttribute(polyt_ct_kernel<LOGG, true>, attr, kY_SmemBytes));
     return NTTB200_OK;
+}
+
+int polyt_prepare() {
+    int rc = polyt_attrs<1>();
+    if (rc == NTTB200_OK) rc = polyt_attrs<2>();
+    if (rc == NTTB200_OK) rc = polyt_attrs<3>();
+    return rc;
 }
 
 static uint32_t py_inv_mod_2_32(uint32_t q) {  // q odd
@@ -395,8 +433,24 @@ static bool polyt_enabled() {
 template <int LOGG, bool DUAL>
 static void polyt_gs_launch(int grid, cudaStream_t st, const CUtensorMap &a_lo, const CUtensorMap &a_hi,
                             const CUtensorMap &b_lo, const CUtensorMap &b_hi, const TileParams &tp,
-                            const CrossTw &cross) {
-    polyt_gs_kernel<LOGG, DUAL><<<grid, kM_Threads, kY_SmemBytes, st>>>(a_lo, a_hi, b_lo, b_hi, tp, cross);
+                            const CrossTw &cross, bool l4) {
+    if (l4) {
+        polyt_gs_kernel<LOGG, DUAL, true><<<grid, kM_Threads, kY_SmemBytes, st>>>(a_lo, a_hi, b_lo, b_hi,
+                                                                                  tp, cross);
+    } else {
+        polyt_gs_kernel<LOGG, DUAL, false><<<grid, kM_Threads, kY_SmemBytes, st>>>(a_lo, a_hi, b_lo, b_hi,
+                                                                                   tp, cross);
+    }
+}
+template <int LOGG>
+static void polyt_ct_launch(int grid, cudaStream_t st, const CUtensorMap &i_lo, const CUtensorMap &i_hi,
+                            const CUtensorMap &o_lo, const CUtensorMap &o_hi, const TileParams &tp,
+                            const CrossTw &cross, bool l4) {
+    if (l4) {
+        polyt_ct_kernel<LOGG, true><<<grid, kM_Threads, kY_SmemBytes, st>>>(i_lo, i_hi, o_lo, o_hi, tp, cross);
+    } else {
+        polyt_ct_kernel<LOGG, false><<<grid, kM_Threads, kY_SmemBytes, st>>>(i_lo, i_hi, o_lo, o_hi, tp, cross);
+    }
 }
 
 // N = 2^13..2^15 golden network in one pass.  d_b != nullptr: input = d_in (*) d_b (Montgomery
@@ -417,6 +471,7 @@ int launch_polyt_gs(nttb200_plan *p, const int32_t *d_in, const int32_t *d_b, in
     tp.q = p->q;
     tp.zero = 0;
     tp.qinv = tp.scale = tp.scale_shoup = 0;
+    tp.four_q = 4u * p->q;
     if (d_b) {
         if (tile_maps(&b_lo, &b_hi, d_b, (size_t) tiles) != NTTB200_OK) return NTTB200_ERR_UNSUPPORTED;
         tp.qinv = py_inv_mod_2_32(p->q);
@@ -430,14 +485,14 @@ int launch_polyt_gs(nttb200_plan *p, const int32_t *d_in, const int32_t *d_b, in
     const uint64_t groups = kM_Teams >> logg;
     const uint64_t ctas = (batch + groups - 1) / groups;
     const int grid = (int) (ctas < (uint64_t) p->sm_count ? ctas : (uint64_t) p->sm_count);
-    const bool dual = d_b != nullptr;
+    const bool dual = d_b != nullptr, l4 = use_l4(p);
     switch (logg * 2 + (dual ? 1 : 0)) {
-        case 2: polyt_gs_launch<1, false>(grid, st, a_lo, a_hi, b_lo, b_hi, tp, p->cross_tw); break;
-        case 3: polyt_gs_launch<1, true>(grid, st, a_lo, a_hi, b_lo, b_hi, tp, p->cross_tw); break;
-        case 4: polyt_gs_launch<2, false>(grid, st, a_lo, a_hi, b_lo, b_hi, tp, p->cross_tw); break;
-        case 5: polyt_gs_launch<2, true>(grid, st, a_lo, a_hi, b_lo, b_hi, tp, p->cross_tw); break;
-        case 6: polyt_gs_launch<3, false>(grid, st, a_lo, a_hi, b_lo, b_hi, tp, p->cross_tw); break;
-        default: polyt_gs_launch<3, true>(grid, st, a_lo, a_hi, b_lo, b_hi, tp, p->cross_tw); break;
+        case 2: polyt_gs_launch<1, false>(grid, st, a_lo, a_hi, b_lo, b_hi, tp, p->cross_tw, l4); break;
+        case 3: polyt_gs_launch<1, true>(grid, st, a_lo, a_hi, b_lo, b_hi, tp, p->cross_tw, l4); break;
+        case 4: polyt_gs_launch<2, false>(grid, st, a_lo, a_hi, b_lo, b_hi, tp, p->cross_tw, l4); break;
+        case 5: polyt_gs_launch<2, true>(grid, st, a_lo, a_hi, b_lo, b_hi, tp, p->cross_tw, l4); break;
+        case 6: polyt_gs_launch<3, false>(grid, st, a_lo, a_hi, b_lo, b_hi, tp, p->cross_tw, l4); break;
+        default: polyt_gs_launch<3, true>(grid, st, a_lo, a_hi, b_lo, b_hi, tp, p->cross_tw, l4); break;
     }
     g_launches.fetch_add(1, std::memory_order_relaxed);
     NTTB200_CUDA(cudaGetLastError());
@@ -464,15 +519,17 @@ int launch_polyt_ct(nttb200_plan *p, const int32_t *d_in, int32_t *d_out, size_t
     tp.q = p->q;
     tp.zero = 0;
     tp.qinv = tp.scale = tp.scale_shoup = 0;
+    tp.four_q = 4u * p->q;
     const uint64_t groups = kM_Teams >> logg;
     const uint64_t ctas = (batch + groups - 1) / groups;
     const int grid = (int) (ctas < (uint64_t) p->sm_count ? ctas : (uint64_t) p->sm_count);
+    const bool l4 = use_l4(p);
     if (logg == 1) {
-        polyt_ct_kernel<1><<<grid, kM_Threads, kY_SmemBytes, st>>>(i_lo, i_hi, o_lo, o_hi, tp, p->cross_tw);
+        polyt_ct_launch<1>(grid, st, i_lo, i_hi, o_lo, o_hi, tp, p->cross_tw, l4);
     } else if (logg == 2) {
-        polyt_ct_kernel<2><<<grid, kM_Threads, kY_SmemBytes, st>>>(i_lo, i_hi, o_lo, o_hi, tp, p->cross_tw);
+        polyt_ct_launch<2>(grid, st, i_lo, i_hi, o_lo, o_hi, tp, p->cross_tw, l4);
     } else {
-        polyt_ct_kernel<3><<<grid, kM_Threads, kY_SmemBytes, st>>>(i_lo, i_hi, o_lo, o_hi, tp, p->cross_tw);
+        polyt_ct_launch<3>(grid, st, i_lo, i_hi, o_lo, o_hi, tp, p->cross_tw, l4);
     }
     g_launches.fetch_add(1, std::memory_order_relaxed);
     NTTB200_CUDA(cudaGetLastError());

@@ -28,8 +28,7 @@
 #include <cuda.h>
 #include <stdlib.h>
 
-#include "fused_common.cuh"
-#include "plan.h"
+#include "tile_common.cuh"
 
 namespace nttb200 {
 
@@ -48,6 +47,7 @@ struct PolymulParams {
     uint32_t qinv;         // q^-1 mod 2^32
     uint32_t scale;        // N^-1 * 2^32 mod q and its Shoup companion
     uint32_t scale_shoup;
+    uint32_t four_q;       // opaque 4q for the 4q-lazy butterflies (q < 2^29)
 };
 
 // CT stage K on registers pairing rows i and i + 2^K of one column, uniform twiddles
@@ -84,13 +84,30 @@ __device__ __forceinline__ void pm_gs_uniform(uint32_t (&v)[64], const UniformTw
     }
 }
 
+// 4q-lazy form (q < 2^29): inputs below 4q whatever the thread (they come out of round 1)
+template <int K>
+__device__ __forceinline__ void pm_gs_uniform_l4(uint32_t (&v)[64], const UniformTw &u, uint32_t q,
+                                                 uint32_t two_q, uint32_t four_q, uint32_t zero) {
+    constexpr int kStride = 1 << K;
+#pragma unroll
+    for (int b = 0; b < (32 >> K); b++) {
+        const uint32_t w = u.w[(32 >> K) + b], wp = u.wp[(32 >> K) + b];
+#pragma unroll
+        for (int e = 0; e < kStride; e++) {
+            int i0 = b * 2 * kStride + e;
+            gs_bfly_l4(l4_bound(K, e, 4), v[i0], v[i0 + kStride], w, wp, q, two_q, four_q, zero);
+        }
+    }
+}
+
 // LOCKSTEP: the loop body is ~90 KB of straight-line code, twice the instruction-cache reach,
 // and 16 warps streaming it at their own pace stall on instruction fetch (ncu: no_instruction
 // 0.88 stall cycles per issue).  Widening the team barriers makes warps run in step and share
 // every fetch: 0 = team (64 threads), 1 = the two teams that share a pair of schedulers
 // (t, t^2), 2 = the four teams of a scheduler pair (t & 1), 3 = the whole CTA.  Modes > 0 need
 // batch % 8 == 0 so that all teams of a CTA have the same trip count.
-template <int LOCKSTEP>
+// L4: 0 classic butterflies, 1 the inverse (GS) half 4q-lazy, 2 both halves.
+template <int LOCKSTEP, int L4 = 0>
 __global__ void __launch_bounds__(kP_Threads, 1)
 polymul4096_kernel(const __grid_constant__ CUtensorMap a_lo, const __grid_constant__ CUtensorMap a_hi,
                    const __grid_constant__ CUtensorMap b_lo, const __grid_constant__ CUtensorMap b_hi,
@@ -104,7 +121,8 @@ polymul4096_kernel(const __grid_constant__ CUtensorMap a_lo, const __grid_consta
     const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);
     const int team = warp >> 1;   // warp-uniform for the compiler (see kernels_fused.cu)
     const int j = tid & 63;
-    const uint32_t q = prm.q, two_q = 2u * prm.q, zero = prm.zero;
+    const uint32_t q = prm.q, two_q = 2u * prm.q, four_q = prm.four_q, zero = prm.zero;
+    constexpr int kBCol = ct_l4_out_n(1, 6), kBRow = ct_l4_out_n(kBCol, 6);   // forward bounds when L4 == 2
 
     if (warp == 0) tmem_alloc_512(tmem_slot);
     if (tid < kP_Teams) mbar_init(bar_base + tid * 8, 1);
@@ -165,12 +183,16 @@ polymul4096_kernel(const __grid_constant__ CUtensorMap a_lo, const __grid_consta
             for (int i = 0; i < 64; i++) {
                 v[i] = lds32(r2_col + i * 128 + (r2_chunk ^ ((i & 7) << 4)));
             }
-            pm_ct_uniform<5, false>(v, uni_fwd, q, two_q, zero);
-            pm_ct_uniform<4, true>(v, uni_fwd, q, two_q, zero);
-            pm_ct_uniform<3, true>(v, uni_fwd, q, two_q, zero);
-            pm_ct_uniform<2, true>(v, uni_fwd, q, two_q, zero);
-            pm_ct_uniform<1, true>(v, uni_fwd, q, two_q, zero);
-            pm_ct_uniform<0, true>(v, uni_fwd, q, two_q, zero);
+            if (L4 == 2) {
+                ct_round_uniform_l4<1>(v, uni_fwd, q, two_q, four_q, zero);
+            } else {
+                pm_ct_uniform<5, false>(v, uni_fwd, q, two_q, zero);
+                pm_ct_uniform<4, true>(v, uni_fwd, q, two_q, zero);
+                pm_ct_uniform<3, true>(v, uni_fwd, q, two_q, zero);
+                pm_ct_uniform<2, true>(v, uni_fwd, q, two_q, zero);
+                pm_ct_uniform<1, true>(v, uni_fwd, q, two_q, zero);
+                pm_ct_uniform<0, true>(v, uni_fwd, q, two_q, zero);
+            }
             // ---- exchange: column write, row read (thread j owns x[64j .. 64j+63])
 #pragma unroll
             for (int i = 0; i < 64; i++) {
@@ -198,19 +220,27 @@ polymul4096_kernel(const __grid_constant__ CUtensorMap a_lo, const __grid_consta
                 }
             }
             // ---- rows: CT stages 5..0, private twiddles from tensor memory
-            ct_round_tmem<true>(v, tw_fwd, q, two_q, zero);
+            if (L4 == 2) {
+                ct_round_tmem_l4<kBCol>(v, tw_fwd, q, two_q, four_q, zero);
+            } else {
+                ct_round_tmem<true>(v, tw_fwd, q, two_q, zero);
+            }
             if (operand == 0) {
                 // a^ canonical, parked in this warp's 64 TMEM columns
 #pragma unroll
                 for (int i = 0; i < 64; i++) {
-                    uint32_t r = min(v[i] - two_q, v[i]);
-                    v[i] = min(r - q, r);
+                    if (L4 == 2) {
+                        v[i] = canon_l4(kBRow, v[i], q, two_q, four_q);
+                    } else {
+                        uint32_t r = min(v[i] - two_q, v[i]);
+                        v[i] = min(r - q, r);
+                    }
                 }
 #pragma unroll
                 for (int g = 0; g < 4; g++) tmem_st16(park + 16 * g, &v[16 * g]);
             }
         }
-        // ---- pointwise: b^ in [0, 2q) times canonical a^ as a Montgomery product in (0, 2q)
+        // ---- pointwise: b^ (any word) times canonical a^ as a Montgomery product in (0, 2q)
         tmem_wait_st();
 #pragma unroll
         for (int g = 0; g < 4; g++) {
@@ -219,14 +249,17 @@ polymul4096_kernel(const __grid_constant__ CUtensorMap a_lo, const __grid_consta
             tmem_wait_ld16(t);
 #pragma unroll
             for (int e = 0; e < 16; e++) {
-                const uint32_t r = min(v[16 * g + e] - two_q, v[16 * g + e]);
-                const uint64_t prod = (uint64_t) r * t[e];
+                const uint64_t prod = (uint64_t) v[16 * g + e] * t[e];   // < 2^32 q: no reduction first
                 const uint32_t m = (uint32_t) prod * prm.qinv;
                 v[16 * g + e] = (uint32_t) (prod >> 32) - __umulhi(m, q) + q;
             }
         }
         // ---- inverse: GS stages 0..5 (private twiddles from tensor memory)
-        gs_round_tmem<true>(v, tw_inv, q, two_q, zero);
+        if (L4) {
+            gs_round_tmem_l4<2>(v, tw_inv, q, two_q, four_q, zero);
+        } else {
+            gs_round_tmem<true>(v, tw_inv, q, two_q, zero);
+        }
 #pragma unroll
         for (int c = 0; c < 16; c++) {
             sts128(r1_row + (c >> 3) * (kF_PolyBytes / 2) + (((c & 7) << 4) ^ r1_xor), v[4 * c],
@@ -247,12 +280,21 @@ polymul4096_kernel(const __grid_constant__ CUtensorMap a_lo, const __grid_consta
             tma_load_3d(buf + kF_PolyBytes / 2, &a_hi, bar, 0, 0, (int) next);
         }
         // ---- GS stages 6..11 (uniform twiddles), N^-1 * 2^32 at the store
-        pm_gs_uniform<0, false>(v, uni_inv, q, two_q, zero);
-        pm_gs_uniform<1, false>(v, uni_inv, q, two_q, zero);
-        pm_gs_uniform<2, false>(v, uni_inv, q, two_q, zero);
-        pm_gs_uniform<3, false>(v, uni_inv, q, two_q, zero);
-        pm_gs_uniform<4, false>(v, uni_inv, q, two_q, zero);
-        pm_gs_uniform<5, true>(v, uni_inv, q, two_q, zero);
+        if (L4) {   // the N^-1 multiplication below accepts any word: no canonicalisation
+            pm_gs_uniform_l4<0>(v, uni_inv, q, two_q, four_q, zero);
+            pm_gs_uniform_l4<1>(v, uni_inv, q, two_q, four_q, zero);
+            pm_gs_uniform_l4<2>(v, uni_inv, q, two_q, four_q, zero);
+            pm_gs_uniform_l4<3>(v, uni_inv, q, two_q, four_q, zero);
+            pm_gs_uniform_l4<4>(v, uni_inv, q, two_q, four_q, zero);
+            pm_gs_uniform_l4<5>(v, uni_inv, q, two_q, four_q, zero);
+        } else {
+            pm_gs_uniform<0, false>(v, uni_inv, q, two_q, zero);
+            pm_gs_uniform<1, false>(v, uni_inv, q, two_q, zero);
+            pm_gs_uniform<2, false>(v, uni_inv, q, two_q, zero);
+            pm_gs_uniform<3, false>(v, uni_inv, q, two_q, zero);
+            pm_gs_uniform<4, false>(v, uni_inv, q, two_q, zero);
+            pm_gs_uniform<5, true>(v, uni_inv, q, two_q, zero);
+        }
         uint32_t *dst = prm.out + (size_t) poly * 4096 + j;
 #pragma unroll
         for (int i = 0; i < 64; i++) {
@@ -274,6 +316,10 @@ int polymul_prepare() {
     NTTB200_CUDA(cudaFuncSetAttribute(polymul4096_kernel<1>, attr, kP_SmemBytes));
     NTTB200_CUDA(cudaFuncSetAttribute(polymul4096_kernel<2>, attr, kP_SmemBytes));
     NTTB200_CUDA(cudaFuncSetAttribute(polymul4096_kernel<3>, attr, kP_SmemBytes));
+    NTTB200_CUDA(cudaFuncSetAttribute(polymul4096_kernel<0, 1>, attr, kP_SmemBytes));
+    NTTB200_CUDA(cudaFuncSetAttribute(polymul4096_kernel<1, 1>, attr, kP_SmemBytes));
+    NTTB200_CUDA(cudaFuncSetAttribute(polymul4096_kernel<0, 2>, attr, kP_SmemBytes));
+    NTTB200_CUDA(cudaFuncSetAttribute(polymul4096_kernel<1, 2>, attr, kP_SmemBytes));
     return NTTB200_OK;
 }
 
@@ -311,14 +357,37 @@ int launch_polymul4096(nttb200_plan *fwd, nttb200_plan *inv, const int32_t *d_a,
     const uint64_t sc = ((uint64_t) inv->n_inv << 32) % inv->q;
     prm.scale = (uint32_t) sc;
     prm.scale_shoup = (uint32_t) ((sc << 32) / inv->q);
+    prm.four_q = 4u * fwd->q;
     const uint64_t ctas = (batch + kP_Teams - 1) / kP_Teams;
     const int grid = (int) (ctas < (uint64_t) fwd->sm_count ? ctas : (uint64_t) fwd->sm_count);
     static const int lockstep = []() {
         const char *e = getenv("NTTB200_POLYMUL_LOCKSTEP");
         return e ? atoi(e) : 1;  // measured: 0 0.458 ms, 1 0.417, 2 0.417, 3 0.423 per 16,384 products
     }();
-    const int mode = batch % kP_Teams == 0 ? lockstep : 0;
-    switch (mode) {
+    int mode = batch % kP_Teams == 0 ? lockstep : 0;
+    static const int l4_level = []() {
+        const char *e = getenv("NTTB200_POLYMUL_L4");
+        return e ? atoi(e) : 2;
+    }();
+    const int l4 = use_l4(fwd) ? l4_level : 0;
+    if (l4 && mode > 1) mode = 1;
+    switch (l4 ? 4 + (l4 - 1) * 2 + mode : mode) {
+        case 4:
+            polymul4096_kernel<0, 1><<<grid, kP_Threads, kP_SmemBytes, st>>>(a_lo, a_hi, b_lo, b_hi,
+                                                                             fwd->uni_gs, inv->uni_gs, prm);
+            break;
+        case 5:
+            polymul4096_kernel<1, 1><<<grid, kP_Threads, kP_SmemBytes, st>>>(a_lo, a_hi, b_lo, b_hi,
+                                                                             fwd->uni_gs, inv->uni_gs, prm);
+            break;
+        case 6:
+            polymul4096_kernel<0, 2><<<grid, kP_Threads, kP_SmemBytes, st>>>(a_lo, a_hi, b_lo, b_hi,
+                                                                             fwd->uni_gs, inv->uni_gs, prm);
+            break;
+        case 7:
+            polymul4096_kernel<1, 2><<<grid, kP_Threads, kP_SmemBytes, st>>>(a_lo, a_hi, b_lo, b_hi,
+                                                                             fwd->uni_gs, inv->uni_gs, prm);
+            break;
         case 1:
             polymul4096_kernel<1><<<grid, kP_Threads, kP_SmemBytes, st>>>(a_lo, a_hi, b_lo, b_hi,
                                                                           fwd->uni_gs, inv->uni_gs, prm);

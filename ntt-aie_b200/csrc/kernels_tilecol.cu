@@ -51,6 +51,7 @@ struct TileColParams {
     uint32_t qinv;
     uint32_t scale;
     uint32_t scale_shoup;
+    uint32_t four_q;       // opaque 4q for the 4q-lazy butterflies (q < 2^29)
 };
 
 // Counter reads are RELAXED (LDG.STRONG.GPU): ld.acquire costs an L1 invalidation
@@ -85,7 +86,10 @@ __device__ __forceinline__ void wait_counter(const uint32_t *ctr, uint32_t targe
 }
 
 // ------------------------------------------------------------------ GS (golden network)
-template <int LOGG, bool DUAL>
+// L4 (q < 2^29): 4q-lazy butterflies; the intermediate between the two item kinds is then
+// left LAZY as well (values below 4q), so a T-item stores its registers as they are and the
+// C-item's first stage does the one conditional subtraction its sums need.
+template <int LOGG, bool DUAL, bool L4>
 __global__ void __launch_bounds__(kM_Threads, 1)
 tilecol_gs_kernel(const __grid_constant__ CUtensorMap map_lo, const __grid_constant__ CUtensorMap map_hi,
                   const __grid_constant__ CUtensorMap map_b_lo,
@@ -103,7 +107,7 @@ tilecol_gs_kernel(const __grid_constant__ CUtensorMap map_lo, const __grid_const
     const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);
     const int team = warp >> 1;
     const int j = tid & 63;
-    const uint32_t q = prm.q, two_q = 2u * prm.q, zero = prm.zero;
+    const uint32_t q = prm.q, two_q = 2u * prm.q, four_q = prm.four_q, zero = prm.zero;
     const uint32_t cta_half = blockIdx.x & (H - 1);
     const uint32_t parity_h = team & 1;
 
@@ -230,7 +234,10 @@ tilecol_gs_kernel(const __grid_constant__ CUtensorMap map_lo, const __grid_const
                         const int t0 = (b2 << (m + 1)) + e;
 #pragma unroll
                         for (int x = 0; x < U * 4; x++) {
-                            if (m == 0) {
+                            if (L4) {
+                                gs_bfly_l4(l4_bound(m, e, 4), w[t0 * U * 4 + x], w[(t0 + (1 << m)) * U * 4 + x],
+                                           cw, cwp, q, two_q, four_q, zero);
+                            } else if (m == 0) {
                                 gs_bfly<false>(w[t0 * U * 4 + x], w[(t0 + 1) * U * 4 + x], cw, cwp, q, two_q,
                                                zero);
                             } else {
@@ -249,8 +256,12 @@ tilecol_gs_kernel(const __grid_constant__ CUtensorMap map_lo, const __grid_const
 #pragma unroll
                     for (int e = 0; e < 4; e++) {
                         uint32_t r = w[(tt * U + u) * 4 + e];
-                        if (DUAL) r = shoup_mul_lazy(r, prm.scale, prm.scale_shoup, q);
-                        o[e] = min(r - q, r);   // every butterfly output is in [0, 2q)
+                        if (DUAL) {
+                            r = shoup_mul_lazy(r, prm.scale, prm.scale_shoup, q);   // any word in
+                        } else if (L4 && !((tt >> (LOGG - 1)) & 1)) {
+                            r = min(r - two_q, r);   // a sum of the last stage: below 4q
+                        }
+                        o[e] = min(r - q, r);   // now in [0, 2q)
                     }
                     *reinterpret_cast<uint4 *>(base + tt * 4096 + u * 256) = make_uint4(o[0], o[1], o[2], o[3]);
                 }
@@ -297,7 +308,11 @@ tilecol_gs_kernel(const __grid_constant__ CUtensorMap map_lo, const __grid_const
                 }
             }
         }
-        gs_round_tmem<DUAL>(v, tw1, q, two_q, zero);
+        if (L4) {
+            gs_round_tmem_l4<(DUAL ? 2 : 1)>(v, tw1, q, two_q, four_q, zero);
+        } else {
+            gs_round_tmem<DUAL>(v, tw1, q, two_q, zero);
+        }
 #pragma unroll
         for (int c = 0; c < 16; c++) {
             sts128(r1_row + (c >> 3) * (kF_PolyBytes / 2) + (((c & 7) << 4) ^ r1_xor), v[4 * c],
@@ -320,11 +335,15 @@ tilecol_gs_kernel(const __grid_constant__ CUtensorMap map_lo, const __grid_const
         }
         publish();
         if (ctr_val < 2 * G) prefetch_counter();   // the next C-item's polynomial was incomplete
-        gs_round<true>(v, tw2, q, two_q, zero);
+        if (L4) {
+            gs_round_l4<4>(v, tw2, q, two_q, four_q, zero);
+        } else {
+            gs_round<true>(v, tw2, q, two_q, zero);
+        }
         uint32_t *dst = prm.out + (size_t) tile_cur * 4096 + j;
 #pragma unroll
         for (int i = 0; i < 64; i++) {
-            dst[i * 64] = min(v[i] - q, v[i]);
+            dst[i * 64] = L4 ? v[i] : min(v[i] - q, v[i]);
         }
         pending = p;
     }
@@ -337,17 +356,22 @@ tilecol_gs_kernel(const __grid_constant__ CUtensorMap map_lo, const __grid_const
 // --------------------------------------------------------------------- host side
 int tile_maps(CUtensorMap *lo, CUtensorMap *hi, const int32_t *base, size_t tiles);  // kernels_fused.cu
 
-int tilecol_prepare() {
+template <int LOGG>
+static int tilecol_attrs() {
     const auto attr = cudaFuncAttributeMaxDynamicSharedMemorySize;
-    NTTB200_CUDA(cudaFuncSetAttribute(tilecol_gs_kernel<1, false>, attr, kTC_SmemBytes));
-    NTTB200_CUDA(cudaFuncSetAttribute(tilecol_gs_kernel<2, false>, attr, kTC_SmemBytes));
-    NTTB200_CUDA(cudaFuncSetAttribute(tilecol_gs_kernel<3, false>, attr, kTC_SmemBytes));
-    NTTB200_CUDA(cudaFuncSetAttribute(tilecol_gs_kernel<4, false>, attr, kTC_SmemBytes));
-    NTTB200_CUDA(cudaFuncSetAttribute(tilecol_gs_kernel<1, true>, attr, kTC_SmemBytes));
-    NTTB200_CUDA(cudaFuncSetAttribute(tilecol_gs_kernel<2, true>, attr, kTC_SmemBytes));
-    NTTB200_CUDA(cudaFuncSetAttribute(tilecol_gs_kernel<3, true>, attr, kTC_SmemBytes));
-    NTTB200_CUDA(cudaFuncSetAttribute(tilecol_gs_kernel<4, true>, attr, kTC_SmemBytes));
+    NTTB200_CUDA(cudaFuncSetAttribute(tilecol_gs_kernel<LOGG, false, false>, attr, kTC_SmemBytes));
+    NTTB200_CUDA(cudaFuncSetAttribute(tilecol_gs_kernel<LOGG, true, false>, attr, kTC_SmemBytes));
+    NTTB200_CUDA(cudaFuncSetAttribute(tilecol_gs_kernel<LOGG, false, true>, attr, kTC_SmemBytes));
+    NTTB200_CUDA(cudaFuncSetAttribute(tilecol_gs_kernel<LOGG, true, true>, attr, kTC_SmemBytes));
     return NTTB200_OK;
+}
+
+int tilecol_prepare() {
+    int rc = tilecol_attrs<1>();
+    if (rc == NTTB200_OK) rc = tilecol_attrs<2>();
+    if (rc == NTTB200_OK) rc = tilecol_attrs<3>();
+    if (rc == NTTB200_OK) rc = tilecol_attrs<4>();
+    return rc;
 }
 
 static uint32_t tc_inv_mod_2_32(uint32_t q) {  // q odd
@@ -379,9 +403,14 @@ static bool tilecol_enabled(uint32_t logn) {
 template <int LOGG, bool DUAL>
 static void tilecol_gs_launch(int grid, cudaStream_t st, const CUtensorMap &a_lo, const CUtensorMap &a_hi,
                               const CUtensorMap &b_lo, const CUtensorMap &b_hi, const TileColParams &tp,
-                              const CrossTw &cross) {
-    tilecol_gs_kernel<LOGG, DUAL><<<grid, kM_Threads, kTC_SmemBytes, st>>>(a_lo, a_hi, b_lo, b_hi, tp,
-                                                                          cross);
+                              const CrossTw &cross, bool l4) {
+    if (l4) {
+        tilecol_gs_kernel<LOGG, DUAL, true><<<grid, kM_Threads, kTC_SmemBytes, st>>>(a_lo, a_hi, b_lo, b_hi,
+                                                                                    tp, cross);
+    } else {
+        tilecol_gs_kernel<LOGG, DUAL, false><<<grid, kM_Threads, kTC_SmemBytes, st>>>(a_lo, a_hi, b_lo, b_hi,
+                                                                                     tp, cross);
+    }
 }
 
 int launch_tilecol_gs(nttb200_plan *p, const int32_t *d_in, const int32_t *d_b, int32_t *d_out,
@@ -407,6 +436,7 @@ int launch_tilecol_gs(nttb200_plan *p, const int32_t *d_in, const int32_t *d_b, 
     tp.q = p->q;
     tp.zero = 0;
     tp.qinv = tp.scale = tp.scale_shoup = 0;
+    tp.four_q = 4u * p->q;
     if (d_b) {
         if (tile_maps(&b_lo, &b_hi, d_b, (size_t) tiles) != NTTB200_OK) return NTTB200_ERR_UNSUPPORTED;
         tp.qinv = tc_inv_mod_2_32(p->q);
@@ -435,16 +465,16 @@ int launch_tilecol_gs(nttb200_plan *p, const int32_t *d_in, const int32_t *d_b, 
     NTTB200_CUDA(cudaMemsetAsync(ctr, 0, sizeof(uint32_t) * (batch + 1), st));
     tp.done = ctr;
     tp.error = ctr + batch;
-    const bool dual = d_b != nullptr;
+    const bool dual = d_b != nullptr, l4 = use_l4(p);
     switch (logg * 2 + (dual ? 1 : 0)) {
-        case 2: tilecol_gs_launch<1, false>(grid, st, a_lo, a_hi, b_lo, b_hi, tp, p->cross_tw); break;
-        case 3: tilecol_gs_launch<1, true>(grid, st, a_lo, a_hi, b_lo, b_hi, tp, p->cross_tw); break;
-        case 4: tilecol_gs_launch<2, false>(grid, st, a_lo, a_hi, b_lo, b_hi, tp, p->cross_tw); break;
-        case 5: tilecol_gs_launch<2, true>(grid, st, a_lo, a_hi, b_lo, b_hi, tp, p->cross_tw); break;
-        case 6: tilecol_gs_launch<3, false>(grid, st, a_lo, a_hi, b_lo, b_hi, tp, p->cross_tw); break;
-        case 7: tilecol_gs_launch<3, true>(grid, st, a_lo, a_hi, b_lo, b_hi, tp, p->cross_tw); break;
-        case 8: tilecol_gs_launch<4, false>(grid, st, a_lo, a_hi, b_lo, b_hi, tp, p->cross_tw); break;
-        default: tilecol_gs_launch<4, true>(grid, st, a_lo, a_hi, b_lo, b_hi, tp, p->cross_tw); break;
+        case 2: tilecol_gs_launch<1, false>(grid, st, a_lo, a_hi, b_lo, b_hi, tp, p->cross_tw, l4); break;
+        case 3: tilecol_gs_launch<1, true>(grid, st, a_lo, a_hi, b_lo, b_hi, tp, p->cross_tw, l4); break;
+        case 4: tilecol_gs_launch<2, false>(grid, st, a_lo, a_hi, b_lo, b_hi, tp, p->cross_tw, l4); break;
+        case 5: tilecol_gs_launch<2, true>(grid, st, a_lo, a_hi, b_lo, b_hi, tp, p->cross_tw, l4); break;
+        case 6: tilecol_gs_launch<3, false>(grid, st, a_lo, a_hi, b_lo, b_hi, tp, p->cross_tw, l4); break;
+        case 7: tilecol_gs_launch<3, true>(grid, st, a_lo, a_hi, b_lo, b_hi, tp, p->cross_tw, l4); break;
+        case 8: tilecol_gs_launch<4, false>(grid, st, a_lo, a_hi, b_lo, b_hi, tp, p->cross_tw, l4); break;
+        default: tilecol_gs_launch<4, true>(grid, st, a_lo, a_hi, b_lo, b_hi, tp, p->cross_tw, l4); break;
     }
     g_launches.fetch_add(1, std::memory_order_relaxed);
     cudaError_t e = cudaGetLastError();

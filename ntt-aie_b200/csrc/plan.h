@@ -80,6 +80,11 @@ int cuda_fail(cudaError_t e, const char *what);
         if (e__ != cudaSuccess) return ::nttb200::cuda_fail(e__, #call); \
     } while (0)
 
+// 4q-lazy kernels (fused_common.cuh, gs_bfly_l4 / ct_bfly_l4) serve moduli whose 8q fits a word.
+// NTTB200_NO_L4=1 is the A/B switch for measurements.
+bool l4_enabled();
+inline bool use_l4(const nttb200_plan *p) { return p->q < (1u << 29) && l4_enabled(); }
+
 // device-side table construction and input canonicalisation (tables.cu)
 int build_shoup_table(nttb200_plan *p, const int32_t *d_table);
 int build_generated_table(nttb200_plan *p, uint32_t kind, uint32_t base, uint32_t gen_logn,

@@ -77,6 +77,103 @@ __device__ __forceinline__ void ct_stage_t(uint32_t (&v)[64], const TW tw, uint3
     }
 }
 
+// 4q-lazy forms (q < 2^29; fused_common.cuh gs_bfly_l4 / ct_bfly_l4)
+template <int S, int BIN0, class TW>
+__device__ __forceinline__ void gs_stage_l4(uint32_t (&v)[64], const TW tw, uint32_t q, uint32_t two_q,
+                                            uint32_t four_q, uint32_t zero) {
+    constexpr int kBlocks = 32 >> S;
+    constexpr int kSlot0 = 32 - (kBlocks >= 2 ? kBlocks : 1);
+    constexpr int kStride = 1 << S;
+#pragma unroll
+    for (int b = 0; b < kBlocks; b += 2) {
+        uint4 t = tw.slot(kSlot0 + b / 2);
+#pragma unroll
+        for (int e = 0; e < kStride; e++) {
+            int i0 = b * 2 * kStride + e;
+            gs_bfly_l4(l4_bound(S, e, BIN0), v[i0], v[i0 + kStride], t.x, t.y, q, two_q, four_q, zero);
+        }
+        if (kBlocks >= 2) {
+#pragma unroll
+            for (int e = 0; e < kStride; e++) {
+                int i0 = (b + 1) * 2 * kStride + e;
+                gs_bfly_l4(l4_bound(S, e, BIN0), v[i0], v[i0 + kStride], t.z, t.w, q, two_q, four_q, zero);
+            }
+        }
+    }
+}
+template <int S, int BIN, class TW>
+__device__ __forceinline__ void ct_stage_l4(uint32_t (&v)[64], const TW tw, uint32_t q, uint32_t two_q,
+                                            uint32_t four_q, uint32_t zero) {
+    constexpr int kBlocks = 32 >> S;
+    constexpr int kSlot0 = 32 - (kBlocks >= 2 ? kBlocks : 1);
+    constexpr int kStride = 1 << S;
+#pragma unroll
+    for (int b = 0; b < kBlocks; b += 2) {
+        uint4 t = tw.slot(kSlot0 + b / 2);
+#pragma unroll
+        for (int e = 0; e < kStride; e++) {
+            int i0 = b * 2 * kStride + e;
+            ct_bfly_l4(BIN, v[i0], v[i0 + kStride], t.x, t.y, q, two_q, four_q, zero);
+        }
+        if (kBlocks >= 2) {
+#pragma unroll
+            for (int e = 0; e < kStride; e++) {
+                int i0 = (b + 1) * 2 * kStride + e;
+                ct_bfly_l4(BIN, v[i0], v[i0 + kStride], t.z, t.w, q, two_q, four_q, zero);
+            }
+        }
+    }
+}
+template <int BIN0, class TW>
+__device__ __forceinline__ void gs_round_l4(uint32_t (&v)[64], const TW tw, uint32_t q, uint32_t two_q,
+                                            uint32_t four_q, uint32_t zero) {
+    gs_stage_l4<0, BIN0>(v, tw, q, two_q, four_q, zero);
+    gs_stage_l4<1, BIN0>(v, tw, q, two_q, four_q, zero);
+    gs_stage_l4<2, BIN0>(v, tw, q, two_q, four_q, zero);
+    gs_stage_l4<3, BIN0>(v, tw, q, two_q, four_q, zero);
+    gs_stage_l4<4, BIN0>(v, tw, q, two_q, four_q, zero);
+    gs_stage_l4<5, BIN0>(v, tw, q, two_q, four_q, zero);
+}
+// inputs below BIN0 * q, outputs below ct_l4_out_n(BIN0, 6) * q (LAST: below 4q)
+template <int BIN0, bool LAST = false, class TW>
+__device__ __forceinline__ void ct_round_l4(uint32_t (&v)[64], const TW tw, uint32_t q, uint32_t two_q,
+                                            uint32_t four_q, uint32_t zero) {
+    constexpr int B5 = BIN0, B4 = ct_l4_out(B5), B3 = ct_l4_out(B4), B2 = ct_l4_out(B3),
+                  B1 = ct_l4_out(B2), B0 = ct_l4_out(B1);
+    ct_stage_l4<5, B5>(v, tw, q, two_q, four_q, zero);
+    ct_stage_l4<4, B4>(v, tw, q, two_q, four_q, zero);
+    ct_stage_l4<3, B3>(v, tw, q, two_q, four_q, zero);
+    ct_stage_l4<2, B2>(v, tw, q, two_q, four_q, zero);
+    ct_stage_l4<1, B1>(v, tw, q, two_q, four_q, zero);
+    ct_stage_l4<0, (LAST ? -B0 : B0)>(v, tw, q, two_q, four_q, zero);
+}
+template <int K, int BIN>
+__device__ __forceinline__ void ct_stage_uniform_l4(uint32_t (&v)[64], const UniformTw &u, uint32_t q,
+                                                    uint32_t two_q, uint32_t four_q, uint32_t zero) {
+    constexpr int kStride = 1 << K;
+#pragma unroll
+    for (int b = 0; b < (32 >> K); b++) {
+        const uint32_t w = u.w[(32 >> K) + b], wp = u.wp[(32 >> K) + b];
+#pragma unroll
+        for (int e = 0; e < kStride; e++) {
+            int i0 = b * 2 * kStride + e;
+            ct_bfly_l4(BIN, v[i0], v[i0 + kStride], w, wp, q, two_q, four_q, zero);
+        }
+    }
+}
+template <int BIN0>
+__device__ __forceinline__ void ct_round_uniform_l4(uint32_t (&v)[64], const UniformTw &u, uint32_t q,
+                                                    uint32_t two_q, uint32_t four_q, uint32_t zero) {
+    constexpr int B5 = BIN0, B4 = ct_l4_out(B5), B3 = ct_l4_out(B4), B2 = ct_l4_out(B3),
+                  B1 = ct_l4_out(B2), B0 = ct_l4_out(B1);
+    ct_stage_uniform_l4<5, B5>(v, u, q, two_q, four_q, zero);
+    ct_stage_uniform_l4<4, B4>(v, u, q, two_q, four_q, zero);
+    ct_stage_uniform_l4<3, B3>(v, u, q, two_q, four_q, zero);
+    ct_stage_uniform_l4<2, B2>(v, u, q, two_q, four_q, zero);
+    ct_stage_uniform_l4<1, B1>(v, u, q, two_q, four_q, zero);
+    ct_stage_uniform_l4<0, B0>(v, u, q, two_q, four_q, zero);
+}
+
 template <int S, bool REDUCE>
 __device__ __forceinline__ void gs_stage_g(uint32_t (&v)[64], const uint4 *tw, uint32_t q,
                                            uint32_t two_q, uint32_t zero) {
@@ -138,6 +235,7 @@ struct TileParams {
     uint32_t qinv;         // q^-1 mod 2^32 (DUAL: Montgomery product of the two inputs)
     uint32_t scale;        // DUAL: every output is multiplied by this constant (Shoup pair)
     uint32_t scale_shoup;
+    uint32_t four_q;       // 4q as an opaque value for the 4q-lazy kernels (q < 2^29), else unused
 };
 
 
