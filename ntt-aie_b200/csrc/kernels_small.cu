@@ -38,12 +38,14 @@ struct SmallParams {
     uint32_t qinv;        // DUAL: q^-1 mod 2^32 (Montgomery product of the two operands)
     uint32_t scale;       // DUAL: every output times this constant (N^-1 * 2^32 mod q) ...
     uint32_t scale_shoup; //       ... and its Shoup companion
+    uint32_t four_q;      // opaque 4q for the 4q-lazy butterflies (q < 2^29)
 };
 
 // round-1 stage (same slot scheme as kernels_fused.cu, 32 lanes per slot)
-template <int S, bool REDUCE0 = false>
+// BIN0 > 0: 4q-lazy form (fused_common.cuh gs_bfly_l4), inputs of the round bounded by BIN0 * q
+template <int S, bool REDUCE0 = false, int BIN0 = 0>
 __device__ __forceinline__ void small_r1_stage(uint32_t (&v)[64], uint32_t tw_addr, uint32_t q,
-                                               uint32_t two_q, uint32_t zero) {
+                                               uint32_t two_q, uint32_t zero, uint32_t four_q = 0) {
     constexpr int kBlocks = 32 >> S;
     constexpr int kSlot0 = 32 - (kBlocks >= 2 ? kBlocks : 1);
     constexpr int kStride = 1 << S;
@@ -53,12 +55,20 @@ __device__ __forceinline__ void small_r1_stage(uint32_t (&v)[64], uint32_t tw_ad
 #pragma unroll
         for (int e = 0; e < kStride; e++) {
             int i0 = b * 2 * kStride + e;
+            if (BIN0 > 0) {
+                gs_bfly_l4(l4_bound(S, e, BIN0), v[i0], v[i0 + kStride], t.x, t.y, q, two_q, four_q, zero);
+                continue;
+            }
             gs_bfly<(S > 0 || REDUCE0)>(v[i0], v[i0 + kStride], t.x, t.y, q, two_q, zero);
         }
         if (kBlocks >= 2) {
 #pragma unroll
             for (int e = 0; e < kStride; e++) {
                 int i0 = (b + 1) * 2 * kStride + e;
+                if (BIN0 > 0) {
+                    gs_bfly_l4(l4_bound(S, e, BIN0), v[i0], v[i0 + kStride], t.z, t.w, q, two_q, four_q, zero);
+                    continue;
+                }
                 gs_bfly<(S > 0 || REDUCE0)>(v[i0], v[i0 + kStride], t.z, t.w, q, two_q, zero);
             }
         }
@@ -67,9 +77,9 @@ __device__ __forceinline__ void small_r1_stage(uint32_t (&v)[64], uint32_t tw_ad
 
 // round-2 stage K on registers v[2*row + col]: pairs rows i and i + 2^K inside each
 // polynomial (RP = 2^(LOGN-6) rows per polynomial); twiddle table[(RP >> (K+1)) + blk]
-template <int LOGN, int K>
+template <int LOGN, int K, bool L4 = false>
 __device__ __forceinline__ void small_r2_stage(uint32_t (&v)[64], const UniformTw &u, uint32_t q,
-                                               uint32_t two_q, uint32_t zero) {
+                                               uint32_t two_q, uint32_t zero, uint32_t four_q = 0) {
     constexpr int RP = 1 << (LOGN - 6);
 #pragma unroll
     for (int i = 0; i < 32; i++) {
@@ -78,7 +88,12 @@ __device__ __forceinline__ void small_r2_stage(uint32_t (&v)[64], const UniformT
         const uint32_t w = u.w[(RP >> (K + 1)) + blk], wp = u.wp[(RP >> (K + 1)) + blk];
 #pragma unroll
         for (int c = 0; c < 2; c++) {
-            gs_bfly<true>(v[2 * i + c], v[2 * (i + (1 << K)) + c], w, wp, q, two_q, zero);
+            if (L4) {   // rows come out of round 1 below 4q whatever the lane
+                gs_bfly_l4(l4_bound(K, i, 4), v[2 * i + c], v[2 * (i + (1 << K)) + c], w, wp, q, two_q,
+                           four_q, zero);
+            } else {
+                gs_bfly<true>(v[2 * i + c], v[2 * (i + (1 << K)) + c], w, wp, q, two_q, zero);
+            }
         }
     }
 }
@@ -86,7 +101,7 @@ __device__ __forceinline__ void small_r2_stage(uint32_t (&v)[64], const UniformT
 // DUAL: the block's input is the pointwise product of two buffers (Montgomery product
 // a*b*2^-32, second operand through the same shared buffer) and every output is
 // multiplied by `scale` -- the tail of a negacyclic multiplication in one kernel.
-template <int LOGN, bool PERMUTE, bool DUAL>
+template <int LOGN, bool PERMUTE, bool DUAL, bool L4 = false>
 __global__ void __launch_bounds__(kS_Threads, 1)
 fused_gs_small_kernel(const __grid_constant__ CUtensorMap map_lo,
                       const __grid_constant__ CUtensorMap map_hi,
@@ -101,7 +116,7 @@ fused_gs_small_kernel(const __grid_constant__ CUtensorMap map_lo,
     const int tid = threadIdx.x;
     const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);  // warp-uniform for the compiler
     const int j = tid & 31;
-    const uint32_t q = prm.q, two_q = 2u * prm.q, zero = prm.zero;
+    const uint32_t q = prm.q, two_q = 2u * prm.q, four_q = prm.four_q, zero = prm.zero;
 
     for (int i = tid; i < 32 * 32; i += kS_Threads) {
         uint4 t = __ldg(prm.tw_r1 + i);
@@ -114,7 +129,7 @@ fused_gs_small_kernel(const __grid_constant__ CUtensorMap map_lo,
     const uint32_t buf = data_base + warp * kS_BlockBytes;
     const uint32_t bar = bar_base + warp * 8;
     const uint64_t stride = (uint64_t) gridDim.x * kS_Warps;
-    uint64_t blk = (uint64_t) blockIdx.x * kS_Warps + warp;
+    uint64_t blk = (uint64_t) warp * gridDim.x + blockIdx.x;   // consecutive blocks on different SMs
     uint32_t parity = 0;
     if (j == 0 && blk < prm.blocks) {
         mbar_expect_tx(bar, kS_BlockBytes);
@@ -163,12 +178,13 @@ fused_gs_small_kernel(const __grid_constant__ CUtensorMap map_lo,
                 }
             }
         }
-        small_r1_stage<0, DUAL>(v, tw_addr, q, two_q, zero);
-        small_r1_stage<1>(v, tw_addr, q, two_q, zero);
-        small_r1_stage<2>(v, tw_addr, q, two_q, zero);
-        small_r1_stage<3>(v, tw_addr, q, two_q, zero);
-        small_r1_stage<4>(v, tw_addr, q, two_q, zero);
-        small_r1_stage<5>(v, tw_addr, q, two_q, zero);
+        constexpr int kB0 = L4 ? (DUAL ? 2 : 1) : 0;
+        small_r1_stage<0, DUAL, kB0>(v, tw_addr, q, two_q, zero, four_q);
+        small_r1_stage<1, false, kB0>(v, tw_addr, q, two_q, zero, four_q);
+        small_r1_stage<2, false, kB0>(v, tw_addr, q, two_q, zero, four_q);
+        small_r1_stage<3, false, kB0>(v, tw_addr, q, two_q, zero, four_q);
+        small_r1_stage<4, false, kB0>(v, tw_addr, q, two_q, zero, four_q);
+        small_r1_stage<5, false, kB0>(v, tw_addr, q, two_q, zero, four_q);
 #pragma unroll
         for (int c = 0; c < 16; c++) {
             sts128(r1_row + (c >> 3) * (kS_BlockBytes / 2) + (((c & 7) << 4) ^ r1_xor), v[4 * c],
@@ -190,11 +206,11 @@ fused_gs_small_kernel(const __grid_constant__ CUtensorMap map_lo,
             tma_load_3d(buf, &map_lo, bar, 0, 0, (int) next);
             tma_load_3d(buf + kS_BlockBytes / 2, &map_hi, bar, 0, 0, (int) next);
         }
-        if (LOGN > 6) small_r2_stage<LOGN, 0>(v, uni, q, two_q, zero);
-        if (LOGN > 7) small_r2_stage<LOGN, 1>(v, uni, q, two_q, zero);
-        if (LOGN > 8) small_r2_stage<LOGN, 2>(v, uni, q, two_q, zero);
-        if (LOGN > 9) small_r2_stage<LOGN, 3>(v, uni, q, two_q, zero);
-        if (LOGN > 10) small_r2_stage<LOGN, 4>(v, uni, q, two_q, zero);
+        if (LOGN > 6) small_r2_stage<LOGN, 0, L4>(v, uni, q, two_q, zero, four_q);
+        if (LOGN > 7) small_r2_stage<LOGN, 1, L4>(v, uni, q, two_q, zero, four_q);
+        if (LOGN > 8) small_r2_stage<LOGN, 2, L4>(v, uni, q, two_q, zero, four_q);
+        if (LOGN > 9) small_r2_stage<LOGN, 3, L4>(v, uni, q, two_q, zero, four_q);
+        if (LOGN > 10) small_r2_stage<LOGN, 4, L4>(v, uni, q, two_q, zero, four_q);
 
         // register (row i, col c) is coefficient 64 i + 2j + c of the block
         uint32_t *dst = prm.out + blk * 2048 + 2 * j;
@@ -208,9 +224,13 @@ fused_gs_small_kernel(const __grid_constant__ CUtensorMap map_lo,
                 row = (b << 1) | (i & 1);
             }
             uint32_t r0 = v[2 * i], r1 = v[2 * i + 1];
-            if (DUAL) {
+            if (DUAL) {   // any word in, [0, 2q) out
                 r0 = shoup_mul_lazy(r0, prm.scale, prm.scale_shoup, q);
                 r1 = shoup_mul_lazy(r1, prm.scale, prm.scale_shoup, q);
+            } else if (L4 && (LOGN == 6 || !((i >> (LOGN - 7)) & 1))) {
+                // a sum of the last stage (or anything out of round 1): below 4q
+                r0 = min(r0 - two_q, r0);
+                r1 = min(r1 - two_q, r1);
             }
             uint2 o;
             o.x = min(r0 - q, r0);
@@ -294,7 +314,7 @@ fused_ct_small_kernel(const __grid_constant__ CUtensorMap map_lo,
     const uint32_t buf = data_base + warp * kS_BlockBytes;
     const uint32_t bar = bar_base + warp * 8;
     const uint64_t stride = (uint64_t) gridDim.x * kS_Warps;
-    uint64_t blk = (uint64_t) blockIdx.x * kS_Warps + warp;
+    uint64_t blk = (uint64_t) warp * gridDim.x + blockIdx.x;   // consecutive blocks on different SMs
     uint32_t parity = 0;
     if (j == 0 && blk < prm.blocks) {
         mbar_expect_tx(bar, kS_BlockBytes);
@@ -383,6 +403,9 @@ static int small_set_attr() {
     NTTB200_CUDA(cudaFuncSetAttribute(fused_gs_small_kernel<LOGN, false, false>, attr, kS_SmemBytes));
     NTTB200_CUDA(cudaFuncSetAttribute(fused_gs_small_kernel<LOGN, true, false>, attr, kS_SmemBytes));
     NTTB200_CUDA(cudaFuncSetAttribute(fused_gs_small_kernel<LOGN, false, true>, attr, kS_SmemBytes));
+    NTTB200_CUDA(cudaFuncSetAttribute(fused_gs_small_kernel<LOGN, false, false, true>, attr, kS_SmemBytes));
+    NTTB200_CUDA(cudaFuncSetAttribute(fused_gs_small_kernel<LOGN, true, false, true>, attr, kS_SmemBytes));
+    NTTB200_CUDA(cudaFuncSetAttribute(fused_gs_small_kernel<LOGN, false, true, true>, attr, kS_SmemBytes));
     NTTB200_CUDA(cudaFuncSetAttribute(fused_ct_small_kernel<LOGN>, attr, kS_SmemBytes));
     return NTTB200_OK;
 }
@@ -434,8 +457,20 @@ static uint32_t small_inv_mod_2_32(uint32_t q) {
 template <int LOGN>
 static void small_launch_t(int kind, int grid, cudaStream_t st, const CUtensorMap &lo,
                            const CUtensorMap &hi, const CUtensorMap &blo, const CUtensorMap &bhi,
-                           const UniformTw &uni, const SmallParams &prm) {
-    switch (kind) {
+                           const UniformTw &uni, const SmallParams &prm, bool l4) {
+    switch (l4 && kind < 3 ? kind + 4 : kind) {
+        case 4:
+            fused_gs_small_kernel<LOGN, false, false, true><<<grid, kS_Threads, kS_SmemBytes, st>>>(
+                lo, hi, lo, hi, uni, prm);
+            break;
+        case 5:
+            fused_gs_small_kernel<LOGN, true, false, true><<<grid, kS_Threads, kS_SmemBytes, st>>>(
+                lo, hi, lo, hi, uni, prm);
+            break;
+        case 6:
+            fused_gs_small_kernel<LOGN, false, true, true><<<grid, kS_Threads, kS_SmemBytes, st>>>(
+                lo, hi, blo, bhi, uni, prm);
+            break;
         case 0:
             fused_gs_small_kernel<LOGN, false, false><<<grid, kS_Threads, kS_SmemBytes, st>>>(
                 lo, hi, lo, hi, uni, prm);
@@ -495,15 +530,18 @@ int launch_small(nttb200_plan *p, int kind, const int32_t *d_in, const int32_t *
         prm.scale = (uint32_t) sc;
         prm.scale_shoup = (uint32_t) ((sc << 32) / p->q);
     }
-    uint64_t ctas = (blocks + kS_Warps - 1) / kS_Warps;
-    int grid = (int) (ctas < (uint64_t) p->sm_count ? ctas : (uint64_t) p->sm_count);
+    prm.four_q = 4u * p->q;
+    // measured at 2^26 coefficients: N = 2048/1024/512 gain 4/4/2 %, N = 256 loses 6 % (two
+    // strided stages cannot amortise the extra canonicalisation step), N <= 128 is HBM-bound
+    const bool l4 = use_l4(p) && p->logn >= 9;
+    int grid = (int) (blocks < (uint64_t) p->sm_count ? blocks : (uint64_t) p->sm_count);
     switch (p->logn) {
-        case 6: small_launch_t<6>(kind, grid, st, lo, hi, blo, bhi, p->uni_gs, prm); break;
-        case 7: small_launch_t<7>(kind, grid, st, lo, hi, blo, bhi, p->uni_gs, prm); break;
-        case 8: small_launch_t<8>(kind, grid, st, lo, hi, blo, bhi, p->uni_gs, prm); break;
-        case 9: small_launch_t<9>(kind, grid, st, lo, hi, blo, bhi, p->uni_gs, prm); break;
-        case 10: small_launch_t<10>(kind, grid, st, lo, hi, blo, bhi, p->uni_gs, prm); break;
-        default: small_launch_t<11>(kind, grid, st, lo, hi, blo, bhi, p->uni_gs, prm); break;
+        case 6: small_launch_t<6>(kind, grid, st, lo, hi, blo, bhi, p->uni_gs, prm, l4); break;
+        case 7: small_launch_t<7>(kind, grid, st, lo, hi, blo, bhi, p->uni_gs, prm, l4); break;
+        case 8: small_launch_t<8>(kind, grid, st, lo, hi, blo, bhi, p->uni_gs, prm, l4); break;
+        case 9: small_launch_t<9>(kind, grid, st, lo, hi, blo, bhi, p->uni_gs, prm, l4); break;
+        case 10: small_launch_t<10>(kind, grid, st, lo, hi, blo, bhi, p->uni_gs, prm, l4); break;
+        default: small_launch_t<11>(kind, grid, st, lo, hi, blo, bhi, p->uni_gs, prm, l4); break;
     }
     g_launches.fetch_add(1, std::memory_order_relaxed);
     NTTB200_CUDA(cudaGetLastError());
