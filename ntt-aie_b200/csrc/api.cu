@@ -751,6 +751,16 @@ int nttb200_rns_polymul_negacyclic(nttb200_rns_plan *fwd, nttb200_rns_plan *inv,
     if (batch == 0) return NTTB200_OK;
     DeviceGuard guard(fwd->device);
     cudaStream_t st = (cudaStream_t) stream;
+    // one kernel per channel: both operands enter the SM once, the product leaves once
+    // (12 N bytes per channel product instead of 28 N through the scratch buffers below)
+    static const bool one_kernel = getenv("NTTB200_RNS_POLYMUL_3KERNEL") == nullptr;
+    if (one_kernel) {
+        int rc1 = NTTB200_OK;
+        for (uint32_t l = 0; l < fwd->limbs && rc1 == NTTB200_OK; l++) {
+            rc1 = launch_polymul4096_strided(fwd->sub[l], inv->sub[l], d_a, d_b, d_c, batch, fwd->limbs, l, st);
+        }
+        if (rc1 != NTTB200_ERR_UNSUPPORTED) return rc1;   // nothing was launched when unsupported (l == 0)
+    }
     const size_t words = batch * fwd->limbs * 4096;
     int32_t *tmp = nullptr;
     NTTB200_CUDA(cudaMallocAsync(&tmp, sizeof(int32_t) * words * 2, st));

@@ -48,6 +48,8 @@ struct PolymulParams {
     uint32_t scale;        // N^-1 * 2^32 mod q and its Shoup companion
     uint32_t scale_shoup;
     uint32_t four_q;       // opaque 4q for the 4q-lazy butterflies (q < 2^29)
+    uint32_t tile_mul;     // product p lives in tile p * tile_mul + tile_off of all three buffers:
+    uint32_t tile_off;     // (1, 0) for plain batches, (L, l) for channel l of an RNS batch
 };
 
 // CT stage K on registers pairing rows i and i + 2^K of one column, uniform twiddles
@@ -151,8 +153,8 @@ polymul4096_kernel(const __grid_constant__ CUtensorMap a_lo, const __grid_consta
     uint32_t parity = 0;
     if (j == 0 && poly < prm.batch) {
         mbar_expect_tx(bar, kF_PolyBytes);
-        tma_load_3d(buf, &a_lo, bar, 0, 0, (int) poly);
-        tma_load_3d(buf + kF_PolyBytes / 2, &a_hi, bar, 0, 0, (int) poly);
+        tma_load_3d(buf, &a_lo, bar, 0, 0, (int) (poly * prm.tile_mul + prm.tile_off));
+        tma_load_3d(buf + kF_PolyBytes / 2, &a_hi, bar, 0, 0, (int) (poly * prm.tile_mul + prm.tile_off));
     }
     // buffer layout as TMA writes it: two halves of [64 rows][32 words], 128 B swizzle
     const uint32_t r1_row = buf + j * 128;
@@ -215,8 +217,8 @@ polymul4096_kernel(const __grid_constant__ CUtensorMap a_lo, const __grid_consta
                 sync();
                 if (j == 0) {
                     mbar_expect_tx(bar, kF_PolyBytes);
-                    tma_load_3d(buf, &b_lo, bar, 0, 0, (int) poly);
-                    tma_load_3d(buf + kF_PolyBytes / 2, &b_hi, bar, 0, 0, (int) poly);
+                    tma_load_3d(buf, &b_lo, bar, 0, 0, (int) (poly * prm.tile_mul + prm.tile_off));
+                    tma_load_3d(buf + kF_PolyBytes / 2, &b_hi, bar, 0, 0, (int) (poly * prm.tile_mul + prm.tile_off));
                 }
             }
             // ---- rows: CT stages 5..0, private twiddles from tensor memory
@@ -276,8 +278,8 @@ polymul4096_kernel(const __grid_constant__ CUtensorMap a_lo, const __grid_consta
         const uint32_t next = poly + stride;
         if (j == 0 && next < prm.batch) {
             mbar_expect_tx(bar, kF_PolyBytes);
-            tma_load_3d(buf, &a_lo, bar, 0, 0, (int) next);
-            tma_load_3d(buf + kF_PolyBytes / 2, &a_hi, bar, 0, 0, (int) next);
+            tma_load_3d(buf, &a_lo, bar, 0, 0, (int) (next * prm.tile_mul + prm.tile_off));
+            tma_load_3d(buf + kF_PolyBytes / 2, &a_hi, bar, 0, 0, (int) (next * prm.tile_mul + prm.tile_off));
         }
         // ---- GS stages 6..11 (uniform twiddles), N^-1 * 2^32 at the store
         if (L4) {   // the N^-1 multiplication below accepts any word: no canonicalisation
@@ -295,7 +297,7 @@ polymul4096_kernel(const __grid_constant__ CUtensorMap a_lo, const __grid_consta
             pm_gs_uniform<4, false>(v, uni_inv, q, two_q, zero);
             pm_gs_uniform<5, true>(v, uni_inv, q, two_q, zero);
         }
-        uint32_t *dst = prm.out + (size_t) poly * 4096 + j;
+        uint32_t *dst = prm.out + ((size_t) poly * prm.tile_mul + prm.tile_off) * 4096 + j;
 #pragma unroll
         for (int i = 0; i < 64; i++) {
             const uint32_t r = shoup_mul_lazy(v[i], prm.scale, prm.scale_shoup, q);
@@ -333,17 +335,25 @@ static uint32_t pm_inv_mod_2_32(uint32_t q) {  // q odd
 // psi^bitrev / psi^-bitrev tables with their N = 4096 layouts built (fused_prepare).
 int launch_polymul4096(nttb200_plan *fwd, nttb200_plan *inv, const int32_t *d_a, const int32_t *d_b,
                        int32_t *d_c, size_t batch, cudaStream_t st) {
+    return launch_polymul4096_strided(fwd, inv, d_a, d_b, d_c, batch, 1, 0, st);
+}
+
+// The same for the products p * tile_mul + tile_off, p < batch, of buffers that hold
+// batch * tile_mul tiles: channel tile_off of an RNS batch [batch][tile_mul][4096].
+int launch_polymul4096_strided(nttb200_plan *fwd, nttb200_plan *inv, const int32_t *d_a,
+                               const int32_t *d_b, int32_t *d_c, size_t batch, uint32_t tile_mul,
+                               uint32_t tile_off, cudaStream_t st) {
     if (fwd->logn != 12 || inv->logn != 12 || !fwd->d_tw_r1 || !inv->d_tw_r1 || !(fwd->q & 1u)) {
         return NTTB200_ERR_UNSUPPORTED;
     }
     if (batch == 0) return NTTB200_OK;
-    if (batch > 0x7fffffffull || ((uintptr_t) d_a & 15u) || ((uintptr_t) d_b & 15u) ||
+    if (batch * tile_mul > 0x7fffffffull || ((uintptr_t) d_a & 15u) || ((uintptr_t) d_b & 15u) ||
         ((uintptr_t) d_c & 3u)) {
         return NTTB200_ERR_UNSUPPORTED;
     }
     CUtensorMap a_lo, a_hi, b_lo, b_hi;
-    if (tile_maps(&a_lo, &a_hi, d_a, batch) != NTTB200_OK ||
-        tile_maps(&b_lo, &b_hi, d_b, batch) != NTTB200_OK) {
+    if (tile_maps(&a_lo, &a_hi, d_a, batch * tile_mul) != NTTB200_OK ||
+        tile_maps(&b_lo, &b_hi, d_b, batch * tile_mul) != NTTB200_OK) {
         return NTTB200_ERR_UNSUPPORTED;
     }
     PolymulParams prm;
@@ -358,6 +368,8 @@ int launch_polymul4096(nttb200_plan *fwd, nttb200_plan *inv, const int32_t *d_a,
     prm.scale = (uint32_t) sc;
     prm.scale_shoup = (uint32_t) ((sc << 32) / inv->q);
     prm.four_q = 4u * fwd->q;
+    prm.tile_mul = tile_mul;
+    prm.tile_off = tile_off;
     const uint64_t ctas = (batch + kP_Teams - 1) / kP_Teams;
     const int grid = (int) (ctas < (uint64_t) fwd->sm_count ? ctas : (uint64_t) fwd->sm_count);
     static const int lockstep = []() {

@@ -112,6 +112,9 @@ int launch_tilecol_gs(nttb200_plan *p, const int32_t *d_in, const int32_t *d_b, 
 int polymul_prepare();
 int launch_polymul4096(nttb200_plan *fwd, nttb200_plan *inv, const int32_t *d_a, const int32_t *d_b,
                        int32_t *d_c, size_t batch, cudaStream_t st);
+int launch_polymul4096_strided(nttb200_plan *fwd, nttb200_plan *inv, const int32_t *d_a,
+                               const int32_t *d_b, int32_t *d_c, size_t batch, uint32_t tile_mul,
+                               uint32_t tile_off, cudaStream_t st);
 
 // generic stage-pass kernels (kernels_generic.cu): stages [sb, se) of the GS
 // (ascending stride) or CT (descending stride) network; permute_out applies the
