@@ -416,6 +416,46 @@ def _psi(n, q):
     raise AssertionError("no 2n-th root found")
 
 
+def test_rns_large_batch(lib, oracle_mod):
+    """A large RNS batch: the transform through the all-channel tile kernel with per-segment
+    tables, the product through one strided launch of the one-kernel product per channel
+    (tile = poly * L + channel): sampled rows against the oracle, in place too.  (Measured and
+    not adopted: one strided launch of the N=4096 transform kernel per channel, 0.611 against
+    0.626 of the HBM roofline for the tile kernel at 8 channels x 8192 polynomials.)"""
+    n, limbs, batch = 4096, 3, 1024 + 5
+    qs = _ntt_primes(limbs - 1) + [Q29]          # the last channel runs the 4q-lazy kernel
+    rng = np.random.default_rng(13100)
+    fwd_t, inv_t = [], []
+    for q in qs:
+        psi = _psi(n, q)
+        fwd_t.append(lib.make_bitrev_table(n, q, psi))
+        inv_t.append(lib.make_bitrev_table(n, q, pow(psi, q - 2, q)))
+    a = np.stack([rng.integers(0, q, (batch, n), dtype=np.int32) for q in qs], axis=1)
+    b = np.stack([rng.integers(0, q, (batch, n), dtype=np.int32) for q in qs], axis=1)
+    a[0] = np.array(qs, dtype=np.int32)[:, None] - 1
+    rows = np.unique(np.concatenate([[0, 1, batch - 1], rng.integers(0, batch, 40)]))
+    d_a, d_b = dev(a), dev(b)
+    d_o = torch.empty_like(d_a)
+    with lib.RnsPlan(qs, fwd_t) as pf, lib.RnsPlan(qs, inv_t) as pi:
+        pi.gs(d_a, d_o, batch)
+        got = d_o.cpu().numpy()
+        for l, q in enumerate(qs):
+            assert np.array_equal(got[rows, l], oracle_mod.ntt_gs(a[rows, l], inv_t[l], q)), ("gs", l)
+        lib.rns_polymul_negacyclic(pf, pi, d_a, d_b, d_o, batch)
+        got = d_o.cpu().numpy()
+        for l, q in enumerate(qs):
+            prod = oracle_mod.pointwise(oracle_mod.ntt_ct(a[rows, l], fwd_t[l], q),
+                                        oracle_mod.ntt_ct(b[rows, l], fwd_t[l], q), q)
+            want = oracle_mod.scale(oracle_mod.ntt_gs(prod, inv_t[l], q),
+                                    oracle_mod.powmod(n, q - 2, q), q)
+            assert np.array_equal(got[rows, l], want), ("polymul", l)
+        assert np.array_equal(d_a.cpu().numpy(), a)
+        pi.gs(d_a, d_a, batch)
+        got = d_a.cpu().numpy()
+        for l, q in enumerate(qs):
+            assert np.array_equal(got[rows, l], oracle_mod.ntt_gs(a[rows, l], inv_t[l], q)), ("in place", l)
+
+
 def test_rns_batches(lib, oracle_mod):
     """N=4096 polynomials in RNS form, [batch][L][4096], one launch for all
     channels, each channel with its own prime and table.  GS and CT per channel against
