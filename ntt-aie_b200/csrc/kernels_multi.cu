@@ -829,6 +829,158 @@ tile_ct_ld_kernel(const uint32_t *__restrict__ in, const __grid_constant__ CUten
     if (j == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
 }
 
+// N = 4096 forward transform with EIGHT teams: 16 KiB input buffer + 8 KiB output staging per
+// team.  The input arrives by TMA and the next tile is prefetched into the input buffer as soon
+// as the rows are in registers (like fused_gs4096_kernel); the output leaves by TMA in two
+// halves through the staging slot: after stage 5 the two 32-word halves of a row are
+// independent, so the left half is finished, staged and handed to the TMA store first, and the
+// store reads the slot while the right half's five stages run -- the slot is free again when
+// the right half wants it.  No second tile buffer, no exposed wait.
+constexpr int kH_Stage = kF_PolyBytes / 2;
+constexpr int kH_TeamBytes = kF_PolyBytes + kH_Stage;   // 24 KiB
+constexpr int kH_SmemBytes = kM_Teams * kH_TeamBytes + kM_TwTile * 16 + 128 + 1024;
+
+template <bool L4>
+__global__ void __launch_bounds__(kM_Threads, 1)
+tile_ct_h_kernel(const __grid_constant__ CUtensorMap map_lo, const __grid_constant__ CUtensorMap map_hi,
+                 const __grid_constant__ CUtensorMap out_lo, const __grid_constant__ CUtensorMap out_hi,
+                 const __grid_constant__ UniformTw uni, const TileParams prm) {
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t data_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    const uint32_t bar_base = data_base + kM_Teams * kH_TeamBytes;
+    const uint32_t tws = bar_base + 128;
+    const int tid = threadIdx.x;
+    const int team = __shfl_sync(0xffffffffu, tid >> 6, 0);
+    const int j = tid & 63;
+    const uint32_t q = prm.q, two_q = 2u * prm.q, four_q = prm.four_q, zero = prm.zero;
+
+    const uint32_t total = prm.batch;  // chunks == 1
+    const uint32_t stride = gridDim.x * kM_Teams;
+    uint32_t tile = team * gridDim.x + blockIdx.x;
+    const uint32_t buf = data_base + team * kH_TeamBytes;   // 1024-byte aligned: 24 KiB = 24 * 1024
+    const uint32_t stg = buf + kF_PolyBytes;
+    const uint32_t bar = bar_base + team * 8;
+    uint32_t parity = 0;
+    if (j == 0) {
+        mbar_init(bar, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        if (tile < total) {
+            mbar_expect_tx(bar, kF_PolyBytes);
+            tma_load_3d(buf, &map_lo, bar, 0, 0, (int) tile);
+            tma_load_3d(buf + kF_PolyBytes / 2, &map_hi, bar, 0, 0, (int) tile);
+        }
+    }
+    for (int i = tid; i < kM_TwTile; i += kM_Threads) {
+        uint4 x = __ldg(prm.tw_tile + i);
+        sts128(tws + i * 16, x.x, x.y, x.z, x.w);
+    }
+    __syncthreads();
+
+    const uint32_t r1_row = buf + j * 128;
+    const uint32_t st_row = stg + j * 128;
+    const uint32_t r1_xor = (j & 7) << 4;
+    const uint32_t r2_col = buf + (j >> 5) * (kF_PolyBytes / 2) + (j & 3) * 4;
+    const uint32_t r2_chunk = ((j & 31) >> 2) << 4;
+    const TwShared twp{tws + j * 16};
+    constexpr int kBCol = ct_l4_out_n(1, 6);                                   // L4 bounds: after the columns,
+    constexpr int kB4 = ct_l4_out(kBCol), kB3 = ct_l4_out(kB4), kB2 = ct_l4_out(kB3),
+                  kB1 = ct_l4_out(kB2), kB0 = ct_l4_out(kB1), kBRow = ct_l4_out(kB0);  // ... per row stage
+
+    for (; tile < total; tile += stride) {
+        uint32_t v[64];
+        mbar_wait(bar, parity);
+        parity ^= 1;
+#pragma unroll
+        for (int i = 0; i < 64; i++) {
+            v[i] = lds32(r2_col + i * 128 + (r2_chunk ^ ((i & 7) << 4)));
+        }
+        // stages 11..6: twiddles table[1..63] from the constant bank
+        if (L4) {
+            ct_round_uniform_l4<1>(v, uni, q, two_q, four_q, zero);
+        } else {
+            ct_stage_uniform<5, false>(v, uni, q, two_q, zero);
+            ct_stage_uniform<4, true>(v, uni, q, two_q, zero);
+            ct_stage_uniform<3, true>(v, uni, q, two_q, zero);
+            ct_stage_uniform<2, true>(v, uni, q, two_q, zero);
+            ct_stage_uniform<1, true>(v, uni, q, two_q, zero);
+            ct_stage_uniform<0, true>(v, uni, q, two_q, zero);
+        }
+#pragma unroll
+        for (int i = 0; i < 64; i++) {
+            asm volatile("st.shared.u32 [%0], %1;" ::"r"(r2_col + i * 128 + (r2_chunk ^ ((i & 7) << 4))),
+                         "r"(v[i])
+                         : "memory");
+        }
+        team_sync(team);
+#pragma unroll
+        for (int c = 0; c < 16; c++) {
+            uint4 t = lds128(r1_row + (c >> 3) * (kF_PolyBytes / 2) + (((c & 7) << 4) ^ r1_xor));
+            v[4 * c + 0] = t.x;
+            v[4 * c + 1] = t.y;
+            v[4 * c + 2] = t.z;
+            v[4 * c + 3] = t.w;
+        }
+        // ---- the input buffer is free: prefetch the next tile; the staging slot is free once the
+        // previous tile's right half has been read by its store
+        fence_proxy_async();
+        if (j == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+        team_sync(team);
+        const uint32_t next = tile + stride;
+        if (j == 0 && next < total) {
+            mbar_expect_tx(bar, kF_PolyBytes);
+            tma_load_3d(buf, &map_lo, bar, 0, 0, (int) next);
+            tma_load_3d(buf + kF_PolyBytes / 2, &map_hi, bar, 0, 0, (int) next);
+        }
+        // ---- rows: stage 5 pairs the halves, stages 4..0 run per half
+        if (L4) {
+            ct_stage_l4<5, kBCol>(v, twp, q, two_q, four_q, zero);
+        } else {
+            ct_stage_t<5, true>(v, twp, q, two_q, zero);
+        }
+#pragma unroll
+        for (int h = 0; h < 2; h++) {
+            if (h == 0) {
+                ct_half_stage<4, 0, (L4 ? kB4 : -1)>(v, twp, q, two_q, four_q, zero);
+                ct_half_stage<3, 0, (L4 ? kB3 : -1)>(v, twp, q, two_q, four_q, zero);
+                ct_half_stage<2, 0, (L4 ? kB2 : -1)>(v, twp, q, two_q, four_q, zero);
+                ct_half_stage<1, 0, (L4 ? kB1 : -1)>(v, twp, q, two_q, four_q, zero);
+                ct_half_stage<0, 0, (L4 ? kB0 : -1)>(v, twp, q, two_q, four_q, zero);
+            } else {
+                ct_half_stage<4, 1, (L4 ? kB4 : -1)>(v, twp, q, two_q, four_q, zero);
+                ct_half_stage<3, 1, (L4 ? kB3 : -1)>(v, twp, q, two_q, four_q, zero);
+                ct_half_stage<2, 1, (L4 ? kB2 : -1)>(v, twp, q, two_q, four_q, zero);
+                ct_half_stage<1, 1, (L4 ? kB1 : -1)>(v, twp, q, two_q, four_q, zero);
+                ct_half_stage<0, 1, (L4 ? kB0 : -1)>(v, twp, q, two_q, four_q, zero);
+                // the left half's store has read the slot while these stages ran
+                if (j == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+                team_sync(team);
+            }
+#pragma unroll
+            for (int c = 0; c < 8; c++) {
+                uint32_t o[4];
+#pragma unroll
+                for (int e = 0; e < 4; e++) {
+                    uint32_t r = v[32 * h + 4 * c + e];
+                    if (L4) {
+                        o[e] = canon_l4(kBRow, r, q, two_q, four_q);
+                    } else {
+                        r = min(r - two_q, r);
+                        o[e] = min(r - q, r);
+                    }
+                }
+                sts128(st_row + ((c << 4) ^ r1_xor), o[0], o[1], o[2], o[3]);
+            }
+            fence_proxy_async();
+            team_sync(team);
+            if (j == 0) {
+                tma_store_3d(h == 0 ? &out_lo : &out_hi, stg, 0, 0, (int) tile);
+                asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+            }
+        }
+    }
+    if (j == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+}
+
 // Forward partner of poly_gs_kernel: N = 2^13..2^15 in one pass.  The cross-tile stages
 // come FIRST in the CT order (largest strides): once the G tiles of a polynomial have
 // landed, every thread gathers its slice of rows from all G tile buffers, runs stages
@@ -1110,6 +1262,8 @@ int multi_set_attrs() {
     NTTB200_CUDA(cudaFuncSetAttribute(tile_gs_kernel<true, true, 2>, attr, kM_SmemBytesTw));
     NTTB200_CUDA(cudaFuncSetAttribute(tile_gs_kernel<true, false, 1>, attr, kM_SmemBytesTw));
     NTTB200_CUDA(cudaFuncSetAttribute(tile_ct_kernel<false, true>, attr, kM_SmemBytesTw));
+    NTTB200_CUDA(cudaFuncSetAttribute(tile_ct_h_kernel<false>, attr, kH_SmemBytes));
+    NTTB200_CUDA(cudaFuncSetAttribute(tile_ct_h_kernel<true>, attr, kH_SmemBytes));
     NTTB200_CUDA(cudaFuncSetAttribute(tile_ct_ld_kernel<false>, attr, kM_SmemBytesTw));
     NTTB200_CUDA(cudaFuncSetAttribute(tile_ct_ld_kernel<true>, attr, kM_SmemBytesTw));
     NTTB200_CUDA(cudaFuncSetAttribute(tile_ct_kernel<false, true, true>, attr, kM_SmemBytesTw));
@@ -1543,9 +1697,22 @@ int launch_multi_ct_mul(nttb200_plan *p, const int32_t *d_in, const int32_t *d_m
     static const bool use_db = getenv("NTTB200_CT_SINGLE_BUFFER") == nullptr;
     static const int ld_mode = []() {   // 0: off, 1: classic butterflies, 2: 4q-lazy where q allows
         const char *e = getenv("NTTB200_CT_LD");
+        return e ? atoi(e) : 0;
+    }();
+    static const int h_mode = []() {    // 0: off, 1: classic butterflies, 2: 4q-lazy where q allows
+        const char *e = getenv("NTTB200_CT_H");
         return e ? atoi(e) : 1;
     }();
-    if (tp.chunks == 1 && ld_mode && !d_mul && p->d_tw_r1 && !((uintptr_t) src & 3u)) {
+    if (tp.chunks == 1 && h_mode && !d_mul && p->d_tw_r1) {
+        const int grid = (int) (tiles < (uint64_t) p->sm_count ? tiles : (uint64_t) p->sm_count);
+        if (h_mode == 2 && use_l4(p)) {
+            tile_ct_h_kernel<true><<<grid, kM_Threads, kH_SmemBytes, st>>>(in_lo, in_hi, out_lo, out_hi,
+                                                                           p->uni_gs, tp);
+        } else {
+            tile_ct_h_kernel<false><<<grid, kM_Threads, kH_SmemBytes, st>>>(in_lo, in_hi, out_lo, out_hi,
+                                                                            p->uni_gs, tp);
+        }
+    } else if (tp.chunks == 1 && ld_mode && !d_mul && p->d_tw_r1 && !((uintptr_t) src & 3u)) {
         const int grid = (int) (tiles < (uint64_t) p->sm_count ? tiles : (uint64_t) p->sm_count);
         if (ld_mode == 2 && use_l4(p)) {
             tile_ct_ld_kernel<true><<<grid, kM_Threads, kM_SmemBytesTw, st>>>(

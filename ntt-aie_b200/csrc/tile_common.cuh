@@ -174,6 +174,33 @@ __device__ __forceinline__ void ct_round_uniform_l4(uint32_t (&v)[64], const Uni
     ct_stage_uniform_l4<0, B0>(v, u, q, two_q, four_q, zero);
 }
 
+// CT stage S < 5 restricted to the registers [32 H, 32 H + 32): after stage 5 the two halves
+// of a 64-coefficient row are independent, which lets a kernel finish and ship one half while
+// the other is still being computed (tile_ct_h_kernel).  BIN < 0: classic butterfly with
+// REDUCE_X = true; BIN > 0: 4q-lazy with input bound BIN.
+template <int S, int H, int BIN, class TW>
+__device__ __forceinline__ void ct_half_stage(uint32_t (&v)[64], const TW tw, uint32_t q, uint32_t two_q,
+                                              uint32_t four_q, uint32_t zero) {
+    static_assert(S < 5, "stage 5 pairs the halves");
+    constexpr int kBlocks = 32 >> S;                 // blocks per row; half H owns kBlocks/2 of them
+    constexpr int kSlot0 = 32 - kBlocks;
+    constexpr int kStride = 1 << S;
+#pragma unroll
+    for (int b = H * (kBlocks / 2); b < (H + 1) * (kBlocks / 2); b++) {
+        const uint4 t = tw.slot(kSlot0 + b / 2);     // (w, w') of blocks b & ~1 and b | 1
+        const uint32_t w = (b & 1) ? t.z : t.x, wp = (b & 1) ? t.w : t.y;
+#pragma unroll
+        for (int e = 0; e < kStride; e++) {
+            const int i0 = b * 2 * kStride + e;
+            if (BIN > 0) {
+                ct_bfly_l4(BIN, v[i0], v[i0 + kStride], w, wp, q, two_q, four_q, zero);
+            } else {
+                ct_bfly<true>(v[i0], v[i0 + kStride], w, wp, q, two_q, zero);
+            }
+        }
+    }
+}
+
 template <int S, bool REDUCE>
 __device__ __forceinline__ void gs_stage_g(uint32_t (&v)[64], const uint4 *tw, uint32_t q,
                                            uint32_t two_q, uint32_t zero) {
