@@ -1701,7 +1701,7 @@ int launch_multi_ct_mul(nttb200_plan *p, const int32_t *d_in, const int32_t *d_m
     }();
     static const int h_mode = []() {    // 0: off, 1: classic butterflies, 2: 4q-lazy where q allows
         const char *e = getenv("NTTB200_CT_H");
-        return e ? atoi(e) : 1;
+        return e ? atoi(e) : 0;   // opt-in until measured on hardware
     }();
     if (tp.chunks == 1 && h_mode && !d_mul && p->d_tw_r1) {
         const int grid = (int) (tiles < (uint64_t) p->sm_count ? tiles : (uint64_t) p->sm_count);
