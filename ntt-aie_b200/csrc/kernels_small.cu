@@ -242,9 +242,10 @@ fused_gs_small_kernel(const __grid_constant__ CUtensorMap map_lo,
 
 
 // round-2-type CT stage K (rows i, i + 2^K of both columns), uniform twiddles
-template <int LOGN, int K, bool REDUCE_X>
+// BIN > 0: 4q-lazy butterfly with input bound BIN (fused_common.cuh ct_bfly_l4)
+template <int LOGN, int K, bool REDUCE_X, int BIN = 0>
 __device__ __forceinline__ void small_ct_col_stage(uint32_t (&v)[64], const UniformTw &u, uint32_t q,
-                                                   uint32_t two_q, uint32_t zero) {
+                                                   uint32_t two_q, uint32_t zero, uint32_t four_q = 0) {
     constexpr int RP = 1 << (LOGN - 6);
 #pragma unroll
     for (int i = 0; i < 32; i++) {
@@ -253,15 +254,19 @@ __device__ __forceinline__ void small_ct_col_stage(uint32_t (&v)[64], const Unif
         const uint32_t w = u.w[(RP >> (K + 1)) + blk], wp = u.wp[(RP >> (K + 1)) + blk];
 #pragma unroll
         for (int c = 0; c < 2; c++) {
-            ct_bfly<REDUCE_X>(v[2 * i + c], v[2 * (i + (1 << K)) + c], w, wp, q, two_q, zero);
+            if (BIN > 0) {
+                ct_bfly_l4(BIN, v[2 * i + c], v[2 * (i + (1 << K)) + c], w, wp, q, two_q, four_q, zero);
+            } else {
+                ct_bfly<REDUCE_X>(v[2 * i + c], v[2 * (i + (1 << K)) + c], w, wp, q, two_q, zero);
+            }
         }
     }
 }
 
 // round-1-type CT stage S on 64 contiguous coefficients, thread-private twiddles
-template <int S, bool REDUCE_X>
+template <int S, bool REDUCE_X, int BIN = 0>
 __device__ __forceinline__ void small_ct_row_stage(uint32_t (&v)[64], uint32_t tw_addr, uint32_t q,
-                                                   uint32_t two_q, uint32_t zero) {
+                                                   uint32_t two_q, uint32_t zero, uint32_t four_q = 0) {
     constexpr int kBlocks = 32 >> S;
     constexpr int kSlot0 = 32 - (kBlocks >= 2 ? kBlocks : 1);
     constexpr int kStride = 1 << S;
@@ -271,12 +276,20 @@ __device__ __forceinline__ void small_ct_row_stage(uint32_t (&v)[64], uint32_t t
 #pragma unroll
         for (int e = 0; e < kStride; e++) {
             int i0 = b * 2 * kStride + e;
+            if (BIN > 0) {
+                ct_bfly_l4(BIN, v[i0], v[i0 + kStride], t.x, t.y, q, two_q, four_q, zero);
+                continue;
+            }
             ct_bfly<REDUCE_X>(v[i0], v[i0 + kStride], t.x, t.y, q, two_q, zero);
         }
         if (kBlocks >= 2) {
 #pragma unroll
             for (int e = 0; e < kStride; e++) {
                 int i0 = (b + 1) * 2 * kStride + e;
+                if (BIN > 0) {
+                    ct_bfly_l4(BIN, v[i0], v[i0 + kStride], t.z, t.w, q, two_q, four_q, zero);
+                    continue;
+                }
                 ct_bfly<REDUCE_X>(v[i0], v[i0 + kStride], t.z, t.w, q, two_q, zero);
             }
         }
@@ -286,7 +299,7 @@ __device__ __forceinline__ void small_ct_row_stage(uint32_t (&v)[64], uint32_t t
 // Forward (Cooley-Tukey) partner, one warp per 2048-coefficient block: columns first
 // (stages logn-1 .. 6, uniform twiddles), warp-synchronous exchange, rows (stages 5 .. 0);
 // the canonical rows leave through a TMA store.
-template <int LOGN>
+template <int LOGN, bool L4 = false>
 __global__ void __launch_bounds__(kS_Threads, 1)
 fused_ct_small_kernel(const __grid_constant__ CUtensorMap map_lo,
                       const __grid_constant__ CUtensorMap map_hi,
@@ -301,7 +314,12 @@ fused_ct_small_kernel(const __grid_constant__ CUtensorMap map_lo,
     const int tid = threadIdx.x;
     const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);
     const int j = tid & 31;
-    const uint32_t q = prm.q, two_q = 2u * prm.q, zero = prm.zero;
+    const uint32_t q = prm.q, two_q = 2u * prm.q, four_q = prm.four_q, zero = prm.zero;
+    // 4q-lazy bounds entering column stage K (4 .. 0, present for K < LOGN - 6) and the rows
+    constexpr int kC4 = 1, kC3 = LOGN > 10 ? ct_l4_out(kC4) : 1, kC2 = LOGN > 9 ? ct_l4_out(kC3) : 1,
+                  kC1 = LOGN > 8 ? ct_l4_out(kC2) : 1, kC0 = LOGN > 7 ? ct_l4_out(kC1) : 1,
+                  kR5 = LOGN > 6 ? ct_l4_out(kC0) : 1, kR4 = ct_l4_out(kR5), kR3 = ct_l4_out(kR4),
+                  kR2 = ct_l4_out(kR3), kR1 = ct_l4_out(kR2), kR0 = ct_l4_out(kR1), kEnd = ct_l4_out(kR0);
 
     for (int i = tid; i < 32 * 32; i += kS_Threads) {
         uint4 t = __ldg(prm.tw_r1 + i);
@@ -339,11 +357,11 @@ fused_ct_small_kernel(const __grid_constant__ CUtensorMap map_lo,
                          : "r"(addr));
         }
         // stages logn-1 .. 6: the first one sees canonical inputs
-        if (LOGN > 10) small_ct_col_stage<LOGN, 4, false>(v, uni, q, two_q, zero);
-        if (LOGN > 9) small_ct_col_stage<LOGN, 3, (LOGN > 10)>(v, uni, q, two_q, zero);
-        if (LOGN > 8) small_ct_col_stage<LOGN, 2, (LOGN > 9)>(v, uni, q, two_q, zero);
-        if (LOGN > 7) small_ct_col_stage<LOGN, 1, (LOGN > 8)>(v, uni, q, two_q, zero);
-        if (LOGN > 6) small_ct_col_stage<LOGN, 0, (LOGN > 7)>(v, uni, q, two_q, zero);
+        if (LOGN > 10) small_ct_col_stage<LOGN, 4, false, (L4 ? kC4 : 0)>(v, uni, q, two_q, zero, four_q);
+        if (LOGN > 9) small_ct_col_stage<LOGN, 3, (LOGN > 10), (L4 ? kC3 : 0)>(v, uni, q, two_q, zero, four_q);
+        if (LOGN > 8) small_ct_col_stage<LOGN, 2, (LOGN > 9), (L4 ? kC2 : 0)>(v, uni, q, two_q, zero, four_q);
+        if (LOGN > 7) small_ct_col_stage<LOGN, 1, (LOGN > 8), (L4 ? kC1 : 0)>(v, uni, q, two_q, zero, four_q);
+        if (LOGN > 6) small_ct_col_stage<LOGN, 0, (LOGN > 7), (L4 ? kC0 : 0)>(v, uni, q, two_q, zero, four_q);
 #pragma unroll
         for (int i = 0; i < 32; i++) {
             uint32_t addr = r2_col + i * 128 + (r2_chunk ^ ((i & 7) << 4));
@@ -359,20 +377,24 @@ fused_ct_small_kernel(const __grid_constant__ CUtensorMap map_lo,
             v[4 * c + 2] = t.z;
             v[4 * c + 3] = t.w;
         }
-        small_ct_row_stage<5, (LOGN > 6)>(v, tw_addr, q, two_q, zero);
-        small_ct_row_stage<4, true>(v, tw_addr, q, two_q, zero);
-        small_ct_row_stage<3, true>(v, tw_addr, q, two_q, zero);
-        small_ct_row_stage<2, true>(v, tw_addr, q, two_q, zero);
-        small_ct_row_stage<1, true>(v, tw_addr, q, two_q, zero);
-        small_ct_row_stage<0, true>(v, tw_addr, q, two_q, zero);
+        small_ct_row_stage<5, (LOGN > 6), (L4 ? kR5 : 0)>(v, tw_addr, q, two_q, zero, four_q);
+        small_ct_row_stage<4, true, (L4 ? kR4 : 0)>(v, tw_addr, q, two_q, zero, four_q);
+        small_ct_row_stage<3, true, (L4 ? kR3 : 0)>(v, tw_addr, q, two_q, zero, four_q);
+        small_ct_row_stage<2, true, (L4 ? kR2 : 0)>(v, tw_addr, q, two_q, zero, four_q);
+        small_ct_row_stage<1, true, (L4 ? kR1 : 0)>(v, tw_addr, q, two_q, zero, four_q);
+        small_ct_row_stage<0, true, (L4 ? kR0 : 0)>(v, tw_addr, q, two_q, zero, four_q);
 #pragma unroll
         for (int c = 0; c < 16; c++) {
             uint32_t o[4];
 #pragma unroll
             for (int e = 0; e < 4; e++) {
                 uint32_t r = v[4 * c + e];
-                r = min(r - two_q, r);
-                o[e] = min(r - q, r);
+                if (L4) {
+                    o[e] = canon_l4(kEnd, r, q, two_q, four_q);
+                } else {
+                    r = min(r - two_q, r);
+                    o[e] = min(r - q, r);
+                }
             }
             sts128(r1_row + (c >> 3) * (kS_BlockBytes / 2) + (((c & 7) << 4) ^ r1_xor), o[0], o[1],
                    o[2], o[3]);
@@ -407,6 +429,7 @@ static int small_set_attr() {
     NTTB200_CUDA(cudaFuncSetAttribute(fused_gs_small_kernel<LOGN, true, false, true>, attr, kS_SmemBytes));
     NTTB200_CUDA(cudaFuncSetAttribute(fused_gs_small_kernel<LOGN, false, true, true>, attr, kS_SmemBytes));
     NTTB200_CUDA(cudaFuncSetAttribute(fused_ct_small_kernel<LOGN>, attr, kS_SmemBytes));
+    NTTB200_CUDA(cudaFuncSetAttribute(fused_ct_small_kernel<LOGN, true>, attr, kS_SmemBytes));
     return NTTB200_OK;
 }
 
@@ -483,10 +506,17 @@ static void small_launch_t(int kind, int grid, cudaStream_t st, const CUtensorMa
             fused_gs_small_kernel<LOGN, false, true><<<grid, kS_Threads, kS_SmemBytes, st>>>(
                 lo, hi, blo, bhi, uni, prm);
             break;
-        default:
-            fused_ct_small_kernel<LOGN><<<grid, kS_Threads, kS_SmemBytes, st>>>(lo, hi, blo, bhi, uni,
-                                                                              prm);
+        default: {
+            static const bool ct_l4 = getenv("NTTB200_SMALL_CT_L4") != nullptr;   // opt-in until measured
+            if (ct_l4 && prm.four_q && prm.q < (1u << 29) && l4_enabled()) {
+                fused_ct_small_kernel<LOGN, true><<<grid, kS_Threads, kS_SmemBytes, st>>>(lo, hi, blo, bhi,
+                                                                                        uni, prm);
+            } else {
+                fused_ct_small_kernel<LOGN><<<grid, kS_Threads, kS_SmemBytes, st>>>(lo, hi, blo, bhi, uni,
+                                                                                  prm);
+            }
             break;
+        }
     }
 }
 

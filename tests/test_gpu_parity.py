@@ -375,11 +375,13 @@ def test_small_n_warp_kernel_ragged_batches(lib, oracle_mod, logn):
 @pytest.mark.parametrize("logn", [10, 12, 14])
 def test_extreme_moduli_on_fast_paths(lib, oracle_mod, logn):
     """q = 2^30 (the largest modulus of the golden's domain, where the lazy ranges
-    [0,2q) / [0,4q) touch 2^32), q = 2 and q = 3 through the register-radix kernels,
-    GS and CT, inputs pinned at q-1."""
+    [0,2q) / [0,4q) touch 2^32), q = 2^29 - 1 and 2^29 - 3 (the largest moduli of the 4q-lazy
+    kernels, whose ranges [0,4q) / [0,8q) touch 2^32 there), q = 2^29 (the first modulus back
+    on the classic kernels), q = 2 and q = 3 through the register-radix kernels, GS and CT,
+    inputs pinned at q-1."""
     n = 1 << logn
     rng = np.random.default_rng(12000 + logn)
-    for q in (1 << 30, (1 << 30) - 35, 2, 3):
+    for q in (1 << 30, (1 << 30) - 35, (1 << 29) - 1, (1 << 29) - 3, 1 << 29, 2, 3):
         table = rng.integers(0, q, n, dtype=np.int32)
         a = rng.integers(0, q, (4, n), dtype=np.int32)
         a[0] = q - 1
@@ -757,6 +759,47 @@ def test_stage_range_empty_batch_and_scatter_limits(lib):
         plan.gs_stage_range(0, 0, 0, 0, 14)
         plan.gs(0, 0, 0)
         plan.ct(0, 0, 0)
+
+
+def test_lazy_range_limits_in_products_and_the_persistent_kernel(lib, oracle_mod):
+    """The 4q-lazy ranges at their limit: q = 2^29 - 3 (8q within 24 of 2^32) and q = 2^29 - 1,
+    tables and inputs pinned at q - 1 / random, through the one-kernel product (N = 4096), the
+    DUAL one-pass product (N = 2^13) and the persistent tile/column kernel (N = 2^16, a batch
+    large enough to take it).  The kernels are table-agnostic, so arbitrary tables stand in for
+    the transform pair; the oracle pipeline is CT, CT, pointwise, GS, N^-1."""
+    rng = np.random.default_rng(20500)
+    for q in ((1 << 29) - 3, (1 << 29) - 1):
+        for logn, batch in ((12, 24), (13, 9)):
+            n = 1 << logn
+            fwd = rng.integers(0, q, n, dtype=np.int32)
+            inv = rng.integers(0, q, n, dtype=np.int32)
+            fwd[1::3] = q - 1
+            inv[1::2] = q - 1
+            a = rng.integers(0, q, (batch, n), dtype=np.int32)
+            b = rng.integers(0, q, (batch, n), dtype=np.int32)
+            a[0] = q - 1
+            b[0] = q - 1
+            b[1] = q - 1
+            prod = oracle_mod.pointwise(oracle_mod.ntt_ct(a, fwd, q), oracle_mod.ntt_ct(b, fwd, q), q)
+            want = oracle_mod.scale(oracle_mod.ntt_gs(prod, inv, q), oracle_mod.powmod(n, q - 2, q), q)
+            with lib.Plan(logn, q, fwd) as pf, lib.Plan(logn, q, inv) as pi:
+                d_c = torch.zeros(batch, n, dtype=torch.int32, device="cuda")
+                lib.polymul_negacyclic(pf, pi, dev(a), dev(b), d_c, batch)
+                assert np.array_equal(d_c.cpu().numpy(), want), (q, logn, pi.last_path)
+        # N = 2^16: 12 tiles per team * 148 SMs * 8 teams / 16 tiles = 888 polynomials at least
+        n, batch = 1 << 16, 896
+        table = rng.integers(0, q, n, dtype=np.int32)
+        table[1::2] = q - 1
+        a = rng.integers(0, q, (batch, n), dtype=np.int32)
+        a[0] = q - 1
+        rows = np.array([0, 1, 500, batch - 1])
+        d_a = dev(a)
+        d_o = torch.empty_like(d_a)
+        with lib.Plan(16, q, table) as plan:
+            plan.gs(d_a, d_o, batch)
+            path = plan.last_path
+        assert np.array_equal(d_o[torch.from_numpy(rows).cuda()].cpu().numpy(),
+                              oracle_mod.ntt_gs(a[rows], table, q)), (q, path)
 
 
 def test_polymul4096_one_kernel(lib, oracle_mod):
