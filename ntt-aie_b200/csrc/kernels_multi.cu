@@ -717,125 +717,16 @@ tile_ct_db_kernel(const __grid_constant__ CUtensorMap map_lo, const __grid_const
     if (j == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
 }
 
-// N = 4096 forward transform, the mirror image of fused_gs4096_kernel: there the input arrives
-// by TMA and the output leaves straight from the registers (coalesced STG.32 columns); here the
-// input comes straight INTO the registers (coalesced LDG.32 columns: lane j of a warp reads
-// word j + 64 i, 128 contiguous bytes per warp instruction) and the output leaves by TMA.  The
-// team's single 16 KiB buffer then only serves the column -> row exchange in the middle of a
-// tile and the output staging at its end; the TMA store drains while the next tile's loads and
-// column stages run, so nothing waits for it and eight teams fit (tile_ct_db_kernel needs two
-// buffers per team for the same overlap and stops at six).  The load latency of a tile is
-// exposed to its own team only; the other teams of the scheduler keep the multiplier busy.
-template <bool L4>
-__global__ void __launch_bounds__(kM_Threads, 1)
-tile_ct_ld_kernel(const uint32_t *__restrict__ in, const __grid_constant__ CUtensorMap out_lo,
-                  const __grid_constant__ CUtensorMap out_hi, const __grid_constant__ UniformTw uni,
-                  const TileParams prm) {
-    extern __shared__ uint8_t smem_raw[];
-    const uint32_t data_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
-    const uint32_t tws = data_base + kM_Teams * kF_PolyBytes;
-    const int tid = threadIdx.x;
-    const int team = __shfl_sync(0xffffffffu, tid >> 6, 0);
-    const int j = tid & 63;
-    const uint32_t q = prm.q, two_q = 2u * prm.q, four_q = prm.four_q, zero = prm.zero;
-
-    for (int i = tid; i < kM_TwTile; i += kM_Threads) {
-        uint4 x = __ldg(prm.tw_tile + i);
-        sts128(tws + i * 16, x.x, x.y, x.z, x.w);
-    }
-    __syncthreads();
-
-    const uint32_t total = prm.batch;  // chunks == 1
-    const uint32_t stride = gridDim.x * kM_Teams;
-    const uint32_t buf = data_base + team * kF_PolyBytes;
-    const uint32_t r1_row = buf + j * 128;
-    const uint32_t r1_xor = (j & 7) << 4;
-    const uint32_t r2_col = buf + (j >> 5) * (kF_PolyBytes / 2) + (j & 3) * 4;
-    const uint32_t r2_chunk = ((j & 31) >> 2) << 4;
-    constexpr int kBCol = ct_l4_out_n(1, 6), kBRow = ct_l4_out_n(kBCol, 6);   // L4 bounds
-
-    for (uint32_t tile = team * gridDim.x + blockIdx.x; tile < total; tile += stride) {
-        uint32_t v[64];
-        const uint32_t *src = in + (size_t) tile * 4096 + j;
-#pragma unroll
-        for (int i = 0; i < 64; i++) {
-            asm volatile("ld.global.L1::no_allocate.u32 %0, [%1];" : "=r"(v[i]) : "l"(src + i * 64));
-        }
-        // the team's next tile starts its way from HBM to L2 now: the loads above then find it there
-        if (j == 0 && tile + stride < total) {
-            asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(in + (size_t) (tile + stride) * 4096),
-                         "n"(kF_PolyBytes)
-                         : "memory");
-        }
-        // stages 11..6: twiddles table[1..63] from the constant bank
-        if (L4) {
-            ct_round_uniform_l4<1>(v, uni, q, two_q, four_q, zero);
-        } else {
-            ct_stage_uniform<5, false>(v, uni, q, two_q, zero);
-            ct_stage_uniform<4, true>(v, uni, q, two_q, zero);
-            ct_stage_uniform<3, true>(v, uni, q, two_q, zero);
-            ct_stage_uniform<2, true>(v, uni, q, two_q, zero);
-            ct_stage_uniform<1, true>(v, uni, q, two_q, zero);
-            ct_stage_uniform<0, true>(v, uni, q, two_q, zero);
-        }
-        // the previous tile's store has read the buffer long ago; make that known to the team
-        if (j == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
-        team_sync(team);
-#pragma unroll
-        for (int i = 0; i < 64; i++) {
-            asm volatile("st.shared.u32 [%0], %1;" ::"r"(r2_col + i * 128 + (r2_chunk ^ ((i & 7) << 4))),
-                         "r"(v[i])
-                         : "memory");
-        }
-        team_sync(team);
-#pragma unroll
-        for (int c = 0; c < 16; c++) {
-            uint4 t = lds128(r1_row + (c >> 3) * (kF_PolyBytes / 2) + (((c & 7) << 4) ^ r1_xor));
-            v[4 * c + 0] = t.x;
-            v[4 * c + 1] = t.y;
-            v[4 * c + 2] = t.z;
-            v[4 * c + 3] = t.w;
-        }
-        if (L4) {
-            ct_round_l4<kBCol>(v, TwShared{tws + j * 16}, q, two_q, four_q, zero);
-        } else {
-            ct_round<true>(v, TwShared{tws + j * 16}, q, two_q, zero);
-        }
-        // every thread rewrites only the row it has just read: no barrier before the staging
-#pragma unroll
-        for (int c = 0; c < 16; c++) {
-            uint32_t o[4];
-#pragma unroll
-            for (int e = 0; e < 4; e++) {
-                uint32_t r = v[4 * c + e];
-                if (L4) {
-                    o[e] = canon_l4(kBRow, r, q, two_q, four_q);
-                } else {
-                    r = min(r - two_q, r);
-                    o[e] = min(r - q, r);
-                }
-            }
-            sts128(r1_row + (c >> 3) * (kF_PolyBytes / 2) + (((c & 7) << 4) ^ r1_xor), o[0], o[1],
-                   o[2], o[3]);
-        }
-        fence_proxy_async();
-        team_sync(team);
-        if (j == 0) {
-            tma_store_3d(&out_lo, buf, 0, 0, (int) tile);
-            tma_store_3d(&out_hi, buf + kF_PolyBytes / 2, 0, 0, (int) tile);
-            asm volatile("cp.async.bulk.commit_group;" ::: "memory");
-        }
-    }
-    if (j == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
-}
-
 // N = 4096 forward transform with EIGHT teams: 16 KiB input buffer + 8 KiB output staging per
 // team.  The input arrives by TMA and the next tile is prefetched into the input buffer as soon
 // as the rows are in registers (like fused_gs4096_kernel); the output leaves by TMA in two
 // halves through the staging slot: after stage 5 the two 32-word halves of a row are
 // independent, so the left half is finished, staged and handed to the TMA store first, and the
 // store reads the slot while the right half's five stages run -- the slot is free again when
-// the right half wants it.  No second tile buffer, no exposed wait.
+// the right half wants it.  No second tile buffer, no exposed wait.  (Measured and dropped: the
+// columns loaded straight into registers with coalesced LDG.32 and an L2 prefetch of the next
+// tile, one buffer per team: 0.547 ms classic / 0.496 ms 4q-lazy -- the load latency stays
+// exposed to the team.)
 constexpr int kH_Stage = kF_PolyBytes / 2;
 constexpr int kH_TeamBytes = kF_PolyBytes + kH_Stage;   // 24 KiB
 constexpr int kH_SmemBytes = kM_Teams * kH_TeamBytes + kM_TwTile * 16 + 128 + 1024;
@@ -1264,8 +1155,6 @@ int multi_set_attrs() {
     NTTB200_CUDA(cudaFuncSetAttribute(tile_ct_kernel<false, true>, attr, kM_SmemBytesTw));
     NTTB200_CUDA(cudaFuncSetAttribute(tile_ct_h_kernel<false>, attr, kH_SmemBytes));
     NTTB200_CUDA(cudaFuncSetAttribute(tile_ct_h_kernel<true>, attr, kH_SmemBytes));
-    NTTB200_CUDA(cudaFuncSetAttribute(tile_ct_ld_kernel<false>, attr, kM_SmemBytesTw));
-    NTTB200_CUDA(cudaFuncSetAttribute(tile_ct_ld_kernel<true>, attr, kM_SmemBytesTw));
     NTTB200_CUDA(cudaFuncSetAttribute(tile_ct_kernel<false, true, true>, attr, kM_SmemBytesTw));
     NTTB200_CUDA(cudaFuncSetAttribute(tile_ct_db_kernel<false>, attr, kD_SmemBytes));
     NTTB200_CUDA(cudaFuncSetAttribute(tile_ct_db_kernel<true>, attr, kD_SmemBytes));
@@ -1695,13 +1584,9 @@ int launch_multi_ct_mul(nttb200_plan *p, const int32_t *d_in, const int32_t *d_m
         tp.qinv = inv_mod_2_32(p->q);
     }
     static const bool use_db = getenv("NTTB200_CT_SINGLE_BUFFER") == nullptr;
-    static const int ld_mode = []() {   // 0: off, 1: classic butterflies, 2: 4q-lazy where q allows
-        const char *e = getenv("NTTB200_CT_LD");
-        return e ? atoi(e) : 0;
-    }();
     static const int h_mode = []() {    // 0: off, 1: classic butterflies, 2: 4q-lazy where q allows
         const char *e = getenv("NTTB200_CT_H");
-        return e ? atoi(e) : 0;   // opt-in until measured on hardware
+        return e ? atoi(e) : 2;   // per 65,536 tiles: 0.515 ms (two buffers, six teams), 0.504, 0.487
     }();
     if (tp.chunks == 1 && h_mode && !d_mul && p->d_tw_r1) {
         const int grid = (int) (tiles < (uint64_t) p->sm_count ? tiles : (uint64_t) p->sm_count);
@@ -1711,15 +1596,6 @@ int launch_multi_ct_mul(nttb200_plan *p, const int32_t *d_in, const int32_t *d_m
         } else {
             tile_ct_h_kernel<false><<<grid, kM_Threads, kH_SmemBytes, st>>>(in_lo, in_hi, out_lo, out_hi,
                                                                             p->uni_gs, tp);
-        }
-    } else if (tp.chunks == 1 && ld_mode && !d_mul && p->d_tw_r1 && !((uintptr_t) src & 3u)) {
-        const int grid = (int) (tiles < (uint64_t) p->sm_count ? tiles : (uint64_t) p->sm_count);
-        if (ld_mode == 2 && use_l4(p)) {
-            tile_ct_ld_kernel<true><<<grid, kM_Threads, kM_SmemBytesTw, st>>>(
-                reinterpret_cast<const uint32_t *>(src), out_lo, out_hi, p->uni_gs, tp);
-        } else {
-            tile_ct_ld_kernel<false><<<grid, kM_Threads, kM_SmemBytesTw, st>>>(
-                reinterpret_cast<const uint32_t *>(src), out_lo, out_hi, p->uni_gs, tp);
         }
     } else if (tp.chunks == 1 && use_db && p->d_tw_r1) {  // d_tw_r1 set <=> uni_gs holds table[1..63]
         uint64_t ctas = (tiles + kD_Teams - 1) / kD_Teams;

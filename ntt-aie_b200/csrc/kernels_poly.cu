@@ -242,7 +242,8 @@ polyt_gs_kernel(const __grid_constant__ CUtensorMap map_lo, const __grid_constan
 // the polynomial after this one; after row stage 5 the two halves of a row are independent,
 // so the left half is finished and handed to the TMA store while the right half's five
 // stages run.  (The first version staged the output in the tile buffer and could only load
-// the next polynomial after the store had drained: the whole load latency was exposed.)
+// the next polynomial after the store had drained -- the whole load latency was exposed:
+// 0.55 / 0.45 / 0.39 of the HBM roofline at N = 2^13 / 2^14 / 2^15 against 0.61 / 0.56 / 0.51.)
 template <int S, int B0, int NB, int BIN, bool L4>
 __device__ __forceinline__ void ct_blocks_sel(uint32_t (&v)[64], const uint32_t *t, uint32_t q,
                                               uint32_t two_q, uint32_t four_q, uint32_t zero) {
@@ -276,7 +277,7 @@ __device__ __forceinline__ void ct_half_tmem(uint32_t (&v)[64], uint32_t taddr, 
 
 template <int LOGG, bool L4>
 __global__ void __launch_bounds__(kM_Threads, 1)
-polyt_cts_kernel(const __grid_constant__ CUtensorMap map_lo, const __grid_constant__ CUtensorMap map_hi,
+polyt_ct_kernel(const __grid_constant__ CUtensorMap map_lo, const __grid_constant__ CUtensorMap map_hi,
                 const __grid_constant__ CUtensorMap out_lo, const __grid_constant__ CUtensorMap out_hi,
                 const TileParams prm, const __grid_constant__ CrossTw cross) {
     constexpr int G = 1 << LOGG;
@@ -459,173 +460,6 @@ polyt_cts_kernel(const __grid_constant__ CUtensorMap map_lo, const __grid_consta
     if (warp == 0) tmem_dealloc_512(tmem_base);
 }
 
-// ---- first version (output staged in the tile buffer), kept until the staged kernel above has
-// been measured on hardware: NTTB200_POLY_CT_STAGED=1 selects the new one
-// Forward partner: the cross-tile stages come FIRST in the CT order (largest strides),
-// then every team finishes its own tile (columns, exchange, rows) and the rows leave
-// through a TMA store.
-template <int LOGG, bool L4>
-__global__ void __launch_bounds__(kM_Threads, 1)
-polyt_ct_kernel(const __grid_constant__ CUtensorMap map_lo, const __grid_constant__ CUtensorMap map_hi,
-                const __grid_constant__ CUtensorMap out_lo, const __grid_constant__ CUtensorMap out_hi,
-                const TileParams prm, const __grid_constant__ CrossTw cross) {
-    constexpr int G = 1 << LOGG;
-    constexpr int kGroups = kM_Teams / G;
-    constexpr int kSlice = 64 / G;
-    extern __shared__ uint8_t smem_raw[];
-    const uint32_t data_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
-    const uint32_t bar_base = data_base + kM_Teams * kF_PolyBytes;
-    const int tid = threadIdx.x;
-    const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);
-    const int team = warp >> 1;
-    const int j = tid & 63;
-    const int grp = team >> LOGG, t = team & (G - 1);
-    const uint32_t q = prm.q, two_q = 2u * prm.q, four_q = prm.four_q, zero = prm.zero;
-
-    uint32_t tmem_base;
-    const uint32_t lane_base = poly_prologue<G>(prm.tw_tile, bar_base, tid, warp, j, tmem_base);
-    const uint32_t tw1 = lane_base + (uint32_t) (t >> 1) * 128u;
-    const Tw16 tw2{bar_base + 128 + (uint32_t) t * 512u};
-
-    const uint32_t buf = data_base + team * kF_PolyBytes;
-    const uint32_t gbuf = data_base + (grp << LOGG) * kF_PolyBytes;
-    const uint32_t bar = bar_base + team * 8;
-    const uint32_t stride = gridDim.x * kGroups;
-    uint32_t poly = blockIdx.x * kGroups + grp;
-    uint32_t parity = 0;
-    if (j == 0 && poly < prm.batch) {
-        mbar_expect_tx(bar, kF_PolyBytes);
-        tma_load_3d(buf, &map_lo, bar, 0, 0, (int) (poly * G + t));
-        tma_load_3d(buf + kF_PolyBytes / 2, &map_hi, bar, 0, 0, (int) (poly * G + t));
-    }
-    const uint32_t r1_row = buf + j * 128;
-    const uint32_t r1_xor = (j & 7) << 4;
-    const uint32_t col_off = (j >> 5) * (kF_PolyBytes / 2) + (j & 3) * 4;  // column j of a tile buffer
-    const uint32_t r2_col = buf + col_off;
-    const uint32_t r2_chunk = ((j & 31) >> 2) << 4;
-    auto group_sync = [&]() {
-        asm volatile("bar.sync %0, %1;" ::"r"(9 + grp), "n"(G * 64) : "memory");
-    };
-
-    for (; poly < prm.batch; poly += stride) {
-        uint32_t v[64];
-        const int tile = (int) (poly * G + t);
-        mbar_wait(bar, parity);
-        parity ^= 1;
-        group_sync();  // all G tiles of the polynomial are in shared memory
-        // ---- cross-tile stages logn-1 .. 12 on rows t*kSlice .. +kSlice-1 of every tile
-#pragma unroll
-        for (int tt = 0; tt < G; tt++) {
-#pragma unroll
-            for (int ii = 0; ii < kSlice; ii++) {
-                const int i = t * kSlice + ii;  // not a compile-time constant: t is per team
-                v[tt * kSlice + ii] = lds32(gbuf + tt * kF_PolyBytes + col_off + i * 128 +
-                                            (r2_chunk ^ ((i & 7) << 4)));
-            }
-        }
-#pragma unroll
-        for (int mm = 0; mm < LOGG; mm++) {
-            const int m = LOGG - 1 - mm;
-#pragma unroll
-            for (int b2 = 0; b2 < (G >> (m + 1)); b2++) {
-                const uint32_t cw = cross.w[(G >> (m + 1)) + b2], cwp = cross.wp[(G >> (m + 1)) + b2];
-#pragma unroll
-                for (int e = 0; e < (1 << m); e++) {
-                    const int t0 = (b2 << (m + 1)) + e;
-#pragma unroll
-                    for (int ii = 0; ii < kSlice; ii++) {
-                        if (L4) {
-                            ct_bfly_l4(ct_l4_out_n(1, mm), v[t0 * kSlice + ii], v[(t0 + (1 << m)) * kSlice + ii],
-                                       cw, cwp, q, two_q, four_q, zero);
-                        } else if (mm == 0) {
-                            ct_bfly<false>(v[t0 * kSlice + ii], v[(t0 + (1 << m)) * kSlice + ii], cw, cwp,
-                                           q, two_q, zero);
-                        } else {
-                            ct_bfly<true>(v[t0 * kSlice + ii], v[(t0 + (1 << m)) * kSlice + ii], cw, cwp,
-                                          q, two_q, zero);
-                        }
-                    }
-                }
-            }
-        }
-#pragma unroll
-        for (int tt = 0; tt < G; tt++) {
-#pragma unroll
-            for (int ii = 0; ii < kSlice; ii++) {
-                const int i = t * kSlice + ii;
-                asm volatile("st.shared.u32 [%0], %1;" ::"r"(gbuf + tt * kF_PolyBytes + col_off + i * 128 +
-                                                             (r2_chunk ^ ((i & 7) << 4))),
-                             "r"(v[tt * kSlice + ii])
-                             : "memory");
-            }
-        }
-        group_sync();
-        // ---- this team's tile: columns (stages 11..6), exchange, rows (stages 5..0)
-#pragma unroll
-        for (int i = 0; i < 64; i++) {
-            v[i] = lds32(r2_col + i * 128 + (r2_chunk ^ ((i & 7) << 4)));
-        }
-        constexpr int kB1 = ct_l4_out_n(1, LOGG), kB2 = ct_l4_out_n(kB1, 6), kB3 = ct_l4_out_n(kB2, 6);
-        if (L4) {
-            ct_round_l4<kB1>(v, tw2, q, two_q, four_q, zero);
-        } else {
-            ct_round<true>(v, tw2, q, two_q, zero);
-        }
-#pragma unroll
-        for (int i = 0; i < 64; i++) {
-            asm volatile("st.shared.u32 [%0], %1;" ::"r"(r2_col + i * 128 + (r2_chunk ^ ((i & 7) << 4))),
-                         "r"(v[i])
-                         : "memory");
-        }
-        team_sync(team);
-#pragma unroll
-        for (int c = 0; c < 16; c++) {
-            uint4 x = lds128(r1_row + (c >> 3) * (kF_PolyBytes / 2) + (((c & 7) << 4) ^ r1_xor));
-            v[4 * c + 0] = x.x;
-            v[4 * c + 1] = x.y;
-            v[4 * c + 2] = x.z;
-            v[4 * c + 3] = x.w;
-        }
-        if (L4) {
-            ct_round_tmem_l4<kB2>(v, tw1, q, two_q, four_q, zero);
-        } else {
-            ct_round_tmem<true>(v, tw1, q, two_q, zero);
-        }
-#pragma unroll
-        for (int c = 0; c < 16; c++) {
-            uint32_t o[4];
-#pragma unroll
-            for (int e = 0; e < 4; e++) {
-                uint32_t r = v[4 * c + e];
-                if (L4) {
-                    o[e] = canon_l4(kB3, r, q, two_q, four_q);
-                } else {
-                    r = min(r - two_q, r);
-                    o[e] = min(r - q, r);
-                }
-            }
-            sts128(r1_row + (c >> 3) * (kF_PolyBytes / 2) + (((c & 7) << 4) ^ r1_xor), o[0], o[1],
-                   o[2], o[3]);
-        }
-        fence_proxy_async();
-        team_sync(team);
-        const uint32_t next = poly + stride;
-        if (j == 0) {
-            tma_store_3d(&out_lo, buf, 0, 0, tile);
-            tma_store_3d(&out_hi, buf + kF_PolyBytes / 2, 0, 0, tile);
-            tma_store_commit_and_wait_read();
-            if (next < prm.batch) {
-                mbar_expect_tx(bar, kF_PolyBytes);
-                tma_load_3d(buf, &map_lo, bar, 0, 0, (int) (next * G + t));
-                tma_load_3d(buf + kF_PolyBytes / 2, &map_hi, bar, 0, 0, (int) (next * G + t));
-            }
-        }
-    }
-    tmem_fence_before_sync();
-    __syncthreads();
-    if (warp == 0) tmem_dealloc_512(tmem_base);
-}
-
 // --------------------------------------------------------------------- host side
 int tile_maps(CUtensorMap *lo, CUtensorMap *hi, const int32_t *base, size_t tiles);  // kernels_fused.cu
 
@@ -636,10 +470,8 @@ static int polyt_attrs() {
     NTTB200_CUDA(cudaFuncSetAttribute(polyt_gs_kernel<LOGG, true, false>, attr, kY_SmemBytes));
     NTTB200_CUDA(cudaFuncSetAttribute(polyt_gs_kernel<LOGG, false, true>, attr, kY_SmemBytes));
     NTTB200_CUDA(cudaFuncSetAttribute(polyt_gs_kernel<LOGG, true, true>, attr, kY_SmemBytes));
-    NTTB200_CUDA(cudaFuncSetAttribute(polyt_ct_kernel<LOGG, false>, attr, kY_SmemBytes));
-    NTTB200_CUDA(cudaFuncSetAttribute(polyt_ct_kernel<LOGG, true>, attr, kY_SmemBytes));
-    NTTB200_CUDA(cudaFuncSetAttribute(polyt_cts_kernel<LOGG, false>, attr, kY_SmemBytesCt));
-    NTTB200_CUDA(cudaFuncSetAttribute(polyt_cts_kernel<LOGG, true>, attr, kY_SmemBytesCt));
+    NTTB200_CUDA(cudaFuncSetAttribute(polyt_ct_kernel<LOGG, false>, attr, kY_SmemBytesCt));
+    NTTB200_CUDA(cudaFuncSetAttribute(polyt_ct_kernel<LOGG, true>, attr, kY_SmemBytesCt));
     return NTTB200_OK;
 }
 
@@ -677,15 +509,10 @@ template <int LOGG>
 static void polyt_ct_launch(int grid, cudaStream_t st, const CUtensorMap &i_lo, const CUtensorMap &i_hi,
                             const CUtensorMap &o_lo, const CUtensorMap &o_hi, const TileParams &tp,
                             const CrossTw &cross, bool l4) {
-    static const bool staged = getenv("NTTB200_POLY_CT_STAGED") != nullptr;
-    if (staged && l4) {
-        polyt_cts_kernel<LOGG, true><<<grid, kM_Threads, kY_SmemBytesCt, st>>>(i_lo, i_hi, o_lo, o_hi, tp, cross);
-    } else if (staged) {
-        polyt_cts_kernel<LOGG, false><<<grid, kM_Threads, kY_SmemBytesCt, st>>>(i_lo, i_hi, o_lo, o_hi, tp, cross);
-    } else if (l4) {
-        polyt_ct_kernel<LOGG, true><<<grid, kM_Threads, kY_SmemBytes, st>>>(i_lo, i_hi, o_lo, o_hi, tp, cross);
+    if (l4) {
+        polyt_ct_kernel<LOGG, true><<<grid, kM_Threads, kY_SmemBytesCt, st>>>(i_lo, i_hi, o_lo, o_hi, tp, cross);
     } else {
-        polyt_ct_kernel<LOGG, false><<<grid, kM_Threads, kY_SmemBytes, st>>>(i_lo, i_hi, o_lo, o_hi, tp, cross);
+        polyt_ct_kernel<LOGG, false><<<grid, kM_Threads, kY_SmemBytesCt, st>>>(i_lo, i_hi, o_lo, o_hi, tp, cross);
     }
 }
 

@@ -28,6 +28,7 @@ constexpr int kS_Threads = kS_Warps * 32;
 constexpr int kS_BlockBytes = 2048 * 4;                 // one warp's block
 constexpr int kS_TwBytes = 32 * 32 * 16;                // [32 slots][32 lanes] uint4
 constexpr int kS_SmemBytes = kS_TwBytes + kS_Warps * kS_BlockBytes + 16 * 8 + 1024;
+constexpr int kS_SmemBytesCt = kS_SmemBytes + kS_Warps * (kS_BlockBytes / 2) + 1024;   // + staging slots
 
 struct SmallParams {
     uint32_t *out;
@@ -296,9 +297,36 @@ __device__ __forceinline__ void small_ct_row_stage(uint32_t (&v)[64], uint32_t t
     }
 }
 
+// stage S < 5 restricted to the registers [32 H, 32 H + 32) (after stage 5 the two halves of a
+// 64-coefficient row are independent)
+template <int S, int H, int BIN>
+__device__ __forceinline__ void small_ct_row_half(uint32_t (&v)[64], uint32_t tw_addr, uint32_t q,
+                                                  uint32_t two_q, uint32_t zero, uint32_t four_q) {
+    constexpr int kBlocks = 32 >> S;
+    constexpr int kSlot0 = 32 - kBlocks;
+    constexpr int kStride = 1 << S;
+#pragma unroll
+    for (int b = H * (kBlocks / 2); b < (H + 1) * (kBlocks / 2); b++) {
+        const uint4 t = lds128(tw_addr + (kSlot0 + b / 2) * (32 * 16));
+        const uint32_t w = (b & 1) ? t.z : t.x, wp = (b & 1) ? t.w : t.y;
+#pragma unroll
+        for (int e = 0; e < kStride; e++) {
+            const int i0 = b * 2 * kStride + e;
+            if (BIN > 0) {
+                ct_bfly_l4(BIN, v[i0], v[i0 + kStride], w, wp, q, two_q, four_q, zero);
+            } else {
+                ct_bfly<true>(v[i0], v[i0 + kStride], w, wp, q, two_q, zero);
+            }
+        }
+    }
+}
+
 // Forward (Cooley-Tukey) partner, one warp per 2048-coefficient block: columns first
 // (stages logn-1 .. 6, uniform twiddles), warp-synchronous exchange, rows (stages 5 .. 0);
-// the canonical rows leave through a TMA store.
+// the canonical rows leave through a TMA store in two halves through a 4 KiB staging slot per
+// warp (see tile_ct_h_kernel, kernels_multi.cu): the block buffer takes the prefetch of the
+// warp's next block as soon as the rows are in registers, and the left half's store drains
+// while the right half's five stages run.
 template <int LOGN, bool L4 = false>
 __global__ void __launch_bounds__(kS_Threads, 1)
 fused_ct_small_kernel(const __grid_constant__ CUtensorMap map_lo,
@@ -311,6 +339,7 @@ fused_ct_small_kernel(const __grid_constant__ CUtensorMap map_lo,
     const uint32_t tw_base = smem_base;
     const uint32_t data_base = smem_base + kS_TwBytes;
     const uint32_t bar_base = data_base + kS_Warps * kS_BlockBytes;
+    const uint32_t stage_base = (bar_base + 16 * 8 + 1023u) & ~1023u;
     const int tid = threadIdx.x;
     const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);
     const int j = tid & 31;
@@ -339,7 +368,9 @@ fused_ct_small_kernel(const __grid_constant__ CUtensorMap map_lo,
         tma_load_3d(buf, &map_lo, bar, 0, 0, (int) blk);
         tma_load_3d(buf + kS_BlockBytes / 2, &map_hi, bar, 0, 0, (int) blk);
     }
+    const uint32_t stg = stage_base + warp * (kS_BlockBytes / 2);
     const uint32_t r1_row = buf + j * 128;
+    const uint32_t st_row = stg + j * 128;
     const uint32_t r1_xor = (j & 7) << 4;
     const uint32_t r2_col = buf + (j >> 4) * (kS_BlockBytes / 2) + (j & 1) * 8;
     const uint32_t r2_chunk = ((j & 15) >> 1) << 4;
@@ -377,43 +408,60 @@ fused_ct_small_kernel(const __grid_constant__ CUtensorMap map_lo,
             v[4 * c + 2] = t.z;
             v[4 * c + 3] = t.w;
         }
-        small_ct_row_stage<5, (LOGN > 6), (L4 ? kR5 : 0)>(v, tw_addr, q, two_q, zero, four_q);
-        small_ct_row_stage<4, true, (L4 ? kR4 : 0)>(v, tw_addr, q, two_q, zero, four_q);
-        small_ct_row_stage<3, true, (L4 ? kR3 : 0)>(v, tw_addr, q, two_q, zero, four_q);
-        small_ct_row_stage<2, true, (L4 ? kR2 : 0)>(v, tw_addr, q, two_q, zero, four_q);
-        small_ct_row_stage<1, true, (L4 ? kR1 : 0)>(v, tw_addr, q, two_q, zero, four_q);
-        small_ct_row_stage<0, true, (L4 ? kR0 : 0)>(v, tw_addr, q, two_q, zero, four_q);
-#pragma unroll
-        for (int c = 0; c < 16; c++) {
-            uint32_t o[4];
-#pragma unroll
-            for (int e = 0; e < 4; e++) {
-                uint32_t r = v[4 * c + e];
-                if (L4) {
-                    o[e] = canon_l4(kEnd, r, q, two_q, four_q);
-                } else {
-                    r = min(r - two_q, r);
-                    o[e] = min(r - q, r);
-                }
-            }
-            sts128(r1_row + (c >> 3) * (kS_BlockBytes / 2) + (((c & 7) << 4) ^ r1_xor), o[0], o[1],
-                   o[2], o[3]);
-        }
+        // ---- the block buffer is free: prefetch the warp's next block; the staging slot is free
+        // once the previous block's right half has been read by its store
         fence_proxy_async();
+        if (j == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
         __syncwarp();
         const uint64_t next = blk + stride;
-        if (j == 0) {
-            tma_store_3d(&out_lo, buf, 0, 0, (int) blk);
-            tma_store_3d(&out_hi, buf + kS_BlockBytes / 2, 0, 0, (int) blk);
-            tma_store_commit_and_wait_read();
-            if (next < prm.blocks) {
-                mbar_expect_tx(bar, kS_BlockBytes);
-                tma_load_3d(buf, &map_lo, bar, 0, 0, (int) next);
-                tma_load_3d(buf + kS_BlockBytes / 2, &map_hi, bar, 0, 0, (int) next);
+        if (j == 0 && next < prm.blocks) {
+            mbar_expect_tx(bar, kS_BlockBytes);
+            tma_load_3d(buf, &map_lo, bar, 0, 0, (int) next);
+            tma_load_3d(buf + kS_BlockBytes / 2, &map_hi, bar, 0, 0, (int) next);
+        }
+        small_ct_row_stage<5, (LOGN > 6), (L4 ? kR5 : 0)>(v, tw_addr, q, two_q, zero, four_q);
+#pragma unroll
+        for (int h = 0; h < 2; h++) {
+            if (h == 0) {
+                small_ct_row_half<4, 0, (L4 ? kR4 : 0)>(v, tw_addr, q, two_q, zero, four_q);
+                small_ct_row_half<3, 0, (L4 ? kR3 : 0)>(v, tw_addr, q, two_q, zero, four_q);
+                small_ct_row_half<2, 0, (L4 ? kR2 : 0)>(v, tw_addr, q, two_q, zero, four_q);
+                small_ct_row_half<1, 0, (L4 ? kR1 : 0)>(v, tw_addr, q, two_q, zero, four_q);
+                small_ct_row_half<0, 0, (L4 ? kR0 : 0)>(v, tw_addr, q, two_q, zero, four_q);
+            } else {
+                small_ct_row_half<4, 1, (L4 ? kR4 : 0)>(v, tw_addr, q, two_q, zero, four_q);
+                small_ct_row_half<3, 1, (L4 ? kR3 : 0)>(v, tw_addr, q, two_q, zero, four_q);
+                small_ct_row_half<2, 1, (L4 ? kR2 : 0)>(v, tw_addr, q, two_q, zero, four_q);
+                small_ct_row_half<1, 1, (L4 ? kR1 : 0)>(v, tw_addr, q, two_q, zero, four_q);
+                small_ct_row_half<0, 1, (L4 ? kR0 : 0)>(v, tw_addr, q, two_q, zero, four_q);
+                // the left half's store has read the slot while these stages ran
+                if (j == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+                __syncwarp();
+            }
+#pragma unroll
+            for (int c = 0; c < 8; c++) {
+                uint32_t o[4];
+#pragma unroll
+                for (int e = 0; e < 4; e++) {
+                    uint32_t r = v[32 * h + 4 * c + e];
+                    if (L4) {
+                        o[e] = canon_l4(kEnd, r, q, two_q, four_q);
+                    } else {
+                        r = min(r - two_q, r);
+                        o[e] = min(r - q, r);
+                    }
+                }
+                sts128(st_row + ((c << 4) ^ r1_xor), o[0], o[1], o[2], o[3]);
+            }
+            fence_proxy_async();
+            __syncwarp();
+            if (j == 0) {
+                tma_store_3d(h == 0 ? &out_lo : &out_hi, stg, 0, 0, (int) blk);
+                asm volatile("cp.async.bulk.commit_group;" ::: "memory");
             }
         }
-        __syncwarp();
     }
+    if (j == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
 }
 
 // --------------------------------------------------------------------- host side
@@ -428,8 +476,8 @@ static int small_set_attr() {
     NTTB200_CUDA(cudaFuncSetAttribute(fused_gs_small_kernel<LOGN, false, false, true>, attr, kS_SmemBytes));
     NTTB200_CUDA(cudaFuncSetAttribute(fused_gs_small_kernel<LOGN, true, false, true>, attr, kS_SmemBytes));
     NTTB200_CUDA(cudaFuncSetAttribute(fused_gs_small_kernel<LOGN, false, true, true>, attr, kS_SmemBytes));
-    NTTB200_CUDA(cudaFuncSetAttribute(fused_ct_small_kernel<LOGN>, attr, kS_SmemBytes));
-    NTTB200_CUDA(cudaFuncSetAttribute(fused_ct_small_kernel<LOGN, true>, attr, kS_SmemBytes));
+    NTTB200_CUDA(cudaFuncSetAttribute(fused_ct_small_kernel<LOGN>, attr, kS_SmemBytesCt));
+    NTTB200_CUDA(cudaFuncSetAttribute(fused_ct_small_kernel<LOGN, true>, attr, kS_SmemBytesCt));
     return NTTB200_OK;
 }
 
@@ -507,12 +555,12 @@ static void small_launch_t(int kind, int grid, cudaStream_t st, const CUtensorMa
                 lo, hi, blo, bhi, uni, prm);
             break;
         default: {
-            static const bool ct_l4 = getenv("NTTB200_SMALL_CT_L4") != nullptr;   // opt-in until measured
-            if (ct_l4 && prm.four_q && prm.q < (1u << 29) && l4_enabled()) {
-                fused_ct_small_kernel<LOGN, true><<<grid, kS_Threads, kS_SmemBytes, st>>>(lo, hi, blo, bhi,
+            // 4q-lazy forward butterflies: N = 512 / 1024 / 2048 0.72 / 0.64 / 0.59 -> 0.73 / 0.68 / 0.62
+            if (l4 && LOGN >= 9) {
+                fused_ct_small_kernel<LOGN, true><<<grid, kS_Threads, kS_SmemBytesCt, st>>>(lo, hi, blo, bhi,
                                                                                         uni, prm);
             } else {
-                fused_ct_small_kernel<LOGN><<<grid, kS_Threads, kS_SmemBytes, st>>>(lo, hi, blo, bhi, uni,
+                fused_ct_small_kernel<LOGN><<<grid, kS_Threads, kS_SmemBytesCt, st>>>(lo, hi, blo, bhi, uni,
                                                                                   prm);
             }
             break;
