@@ -19,6 +19,40 @@
 namespace nttb200 {
 
 std::atomic<uint64_t> g_launches{0};
+
+static std::mutex g_pool_mu;
+static cudaMemPool_t g_pool[64] = {};
+static std::atomic<int> g_live_plans{0};
+
+int scratch_alloc_async(void **p, size_t bytes, cudaStream_t st) {
+    int dev = 0;
+    NTTB200_CUDA(cudaGetDevice(&dev));
+    if (dev < 0 || dev >= 64) return NTTB200_ERR_UNSUPPORTED;
+    cudaMemPool_t pool;
+    {
+        std::lock_guard<std::mutex> lock(g_pool_mu);
+        if (!g_pool[dev]) {
+            cudaMemPoolProps props = {};
+            props.allocType = cudaMemAllocationTypePinned;
+            props.handleTypes = cudaMemHandleTypeNone;
+            props.location.type = cudaMemLocationTypeDevice;
+            props.location.id = dev;
+            NTTB200_CUDA(cudaMemPoolCreate(&g_pool[dev], &props));
+            uint64_t keep = ~0ull;
+            NTTB200_CUDA(cudaMemPoolSetAttribute(g_pool[dev], cudaMemPoolAttrReleaseThreshold, &keep));
+        }
+        pool = g_pool[dev];
+    }
+    NTTB200_CUDA(cudaMallocFromPoolAsync(p, bytes, pool, st));
+    return NTTB200_OK;
+}
+
+static void scratch_trim_all() {
+    std::lock_guard<std::mutex> lock(g_pool_mu);
+    for (int d = 0; d < 64; d++) {
+        if (g_pool[d]) cudaMemPoolTrimTo(g_pool[d], 0);
+    }
+}
 static thread_local char t_err[512] = "";
 
 int cuda_fail(cudaError_t e, const char *what) {
@@ -202,6 +236,7 @@ static int plan_finish(nttb200_plan **out, nttb200_plan *p) {
         plan_abort(p);
         return rc;
     }
+    g_live_plans.fetch_add(1);
     *out = p;
     return NTTB200_OK;
 }
@@ -287,6 +322,7 @@ int nttb200_plan_destroy(nttb200_plan *p) {
     multi_release(p);
     if (p->d_tw) cudaFree(p->d_tw);
     delete p;
+    if (g_live_plans.fetch_sub(1) == 1) scratch_trim_all();   // last plan: give the scratch pages back
     return NTTB200_OK;
 }
 
@@ -620,7 +656,10 @@ int nttb200_polymul_negacyclic(nttb200_plan *fwd, nttb200_plan *inv, const int32
     if (fast) {
         // NTT(a), NTT(b) into scratch; pointwise product, inverse transform and the
         // N^-1 scaling in one pass over them
-        NTTB200_CUDA(cudaMallocAsync(&tmp, sizeof(int32_t) * words * 2, st));
+        {
+        int rca = scratch_alloc_async((void **) &tmp, sizeof(int32_t) * words * 2, st);
+        if (rca != NTTB200_OK) return rca;
+    }
         int rc = launch_multi_ct(fwd, d_a, tmp, batch, st);
         if (rc == NTTB200_OK && fwd->logn == 12 && inv->d_tw_r1 && !getenv("NTTB200_POLYMUL_DUAL")) {
             // N = 4096: the pointwise product rides on the second forward transform (its
@@ -641,7 +680,10 @@ int nttb200_polymul_negacyclic(nttb200_plan *fwd, nttb200_plan *inv, const int32
     if (!((fwd->flags | inv->flags) & NTTB200_FORCE_GENERIC) && fwd->logn >= 6 && fwd->logn <= 11 &&
         fwd->d_tw_r1 && inv->d_tw_r1 && batch % ((size_t) 2048 >> fwd->logn) == 0) {
         // N = 512..2048: warp-per-block CT, CT, then pointwise + inverse + scaling in one kernel
-        NTTB200_CUDA(cudaMallocAsync(&tmp, sizeof(int32_t) * words * 2, st));
+        {
+        int rca = scratch_alloc_async((void **) &tmp, sizeof(int32_t) * words * 2, st);
+        if (rca != NTTB200_OK) return rca;
+    }
         size_t done = 0;
         int rc = launch_small(fwd, 3, d_a, nullptr, tmp, batch, st, &done);
         if (rc == NTTB200_OK) rc = launch_small(fwd, 3, d_b, nullptr, tmp + words, batch, st, &done);
@@ -653,7 +695,10 @@ int nttb200_polymul_negacyclic(nttb200_plan *fwd, nttb200_plan *inv, const int32
         }
         tmp = nullptr;
     }
-    NTTB200_CUDA(cudaMallocAsync(&tmp, sizeof(int32_t) * words, st));
+    {
+        int rca = scratch_alloc_async((void **) &tmp, sizeof(int32_t) * words, st);
+        if (rca != NTTB200_OK) return rca;
+    }
     int rc = launch_generic(fwd, d_b, tmp, batch, 0, (int) fwd->logn, true, false, st);
     if (rc == NTTB200_OK) rc = launch_generic(fwd, d_a, d_c, batch, 0, (int) fwd->logn, true, false, st);
     if (rc == NTTB200_OK) rc = launch_pointwise(fwd, d_c, tmp, d_c, words, st);
@@ -763,7 +808,10 @@ int nttb200_rns_polymul_negacyclic(nttb200_rns_plan *fwd, nttb200_rns_plan *inv,
     }
     const size_t words = batch * fwd->limbs * 4096;
     int32_t *tmp = nullptr;
-    NTTB200_CUDA(cudaMallocAsync(&tmp, sizeof(int32_t) * words * 2, st));
+    {
+        int rca = scratch_alloc_async((void **) &tmp, sizeof(int32_t) * words * 2, st);
+        if (rca != NTTB200_OK) return rca;
+    }
     int rc = rns_run(fwd, 1, d_a, nullptr, tmp, batch, stream);
     if (rc == NTTB200_OK) rc = rns_run(fwd, 1, d_b, nullptr, tmp + words, batch, stream);
     if (rc == NTTB200_OK) rc = rns_run(inv, 2, tmp, tmp + words, d_c, batch, stream);

@@ -77,6 +77,7 @@ polyt_gs_kernel(const __grid_constant__ CUtensorMap map_lo, const __grid_constan
     extern __shared__ uint8_t smem_raw[];
     const uint32_t data_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
     const uint32_t bar_base = data_base + kM_Teams * kF_PolyBytes;
+    const uint32_t park_base = (data_base + kY_StageBase + 1023u) & ~1023u;   // G = 2: 8 KiB per team
     const int tid = threadIdx.x;
     const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);
     const int team = warp >> 1;
@@ -159,7 +160,21 @@ polyt_gs_kernel(const __grid_constant__ CUtensorMap map_lo, const __grid_constan
         for (int i = 0; i < 64; i++) {
             v[i] = lds32(r2_col + i * 128 + (r2_chunk ^ ((i & 7) << 4)));
         }
-        team_sync(team);
+        const uint32_t next = poly + stride;
+        if constexpr (LOGG == 1) {
+            // G = 2 exchanges its third round through separate parking slots (below), so the tile
+            // buffer is free here and takes the next tile while rounds 2 and 3 run -- as in the
+            // N = 4096 kernel
+            fence_proxy_async();
+            team_sync(team);
+            if (j == 0 && next < prm.batch) {
+                mbar_expect_tx(bar, kF_PolyBytes);
+                tma_load_3d(buf, &map_lo, bar, 0, 0, (int) (next * G + t));
+                tma_load_3d(buf + kF_PolyBytes / 2, &map_hi, bar, 0, 0, (int) (next * G + t));
+            }
+        } else {
+            team_sync(team);
+        }
         // ---- round 2: stages 6..11, the position's 63 pairs from shared memory
         if (L4) {
             gs_round_l4<4>(v, tw2, q, two_q, four_q, zero);
@@ -167,6 +182,63 @@ polyt_gs_kernel(const __grid_constant__ CUtensorMap map_lo, const __grid_constan
             gs_round<true>(v, tw2, q, two_q, zero);
         }
 
+        if constexpr (LOGG == 1) {
+            // ---- round 3, two tiles: stage 12 pairs a[j + 64 i] of tile 0 with the same element of
+            // tile 1.  Team t keeps rows 32 t .. 32 t + 31 of its own tile and receives the same
+            // rows of the other tile: half the exchange of the general scheme, through an 8 KiB
+            // slot per team (slot[ii][j]), and the tile buffer stays out of it.
+            const uint32_t my_slot = park_base + (uint32_t) team * (kF_PolyBytes / 2) + j * 4;
+            const uint32_t his_slot = park_base + (uint32_t) (team ^ 1) * (kF_PolyBytes / 2) + j * 4;
+            uint32_t u[32];
+            const uint32_t cw = cross.w[1], cwp = cross.wp[1];
+            uint32_t *dst = prm.out + ((size_t) poly << 13) + j;
+            auto finish = [&](uint32_t x, uint32_t y, int row) {   // x: tile 0 (a sum), y: tile 1 (a product)
+                if (DUAL) {
+                    x = shoup_mul_lazy(x, prm.scale, prm.scale_shoup, q);   // any word in, [0, 2q) out
+                    y = shoup_mul_lazy(y, prm.scale, prm.scale_shoup, q);
+                } else if (L4) {
+                    x = min(x - two_q, x);   // sums of the last stage are below 4q
+                }
+                dst[row * 64] = min(x - q, x);
+                dst[4096 + row * 64] = min(y - q, y);
+            };
+            if (t == 0) {
+#pragma unroll
+                for (int ii = 0; ii < 32; ii++) {
+                    asm volatile("st.shared.u32 [%0], %1;" ::"r"(my_slot + ii * 256), "r"(v[32 + ii]) : "memory");
+                }
+            } else {
+#pragma unroll
+                for (int ii = 0; ii < 32; ii++) {
+                    asm volatile("st.shared.u32 [%0], %1;" ::"r"(my_slot + ii * 256), "r"(v[ii]) : "memory");
+                }
+            }
+            group_sync();
+#pragma unroll
+            for (int ii = 0; ii < 32; ii++) u[ii] = lds32(his_slot + ii * 256);
+            group_sync();   // the other team may refill its slot only after this
+            if (t == 0) {
+#pragma unroll
+                for (int ii = 0; ii < 32; ii++) {
+                    if (L4) {
+                        gs_bfly_l4(4, v[ii], u[ii], cw, cwp, q, two_q, four_q, zero);
+                    } else {
+                        gs_bfly<true>(v[ii], u[ii], cw, cwp, q, two_q, zero);
+                    }
+                    finish(v[ii], u[ii], ii);
+                }
+            } else {
+#pragma unroll
+                for (int ii = 0; ii < 32; ii++) {
+                    if (L4) {
+                        gs_bfly_l4(4, u[ii], v[32 + ii], cw, cwp, q, two_q, four_q, zero);
+                    } else {
+                        gs_bfly<true>(u[ii], v[32 + ii], cw, cwp, q, two_q, zero);
+                    }
+                    finish(u[ii], v[32 + ii], 32 + ii);
+                }
+            }
+        } else {
         // ---- round 3: register i is a[t*4096 + j + 64 i].  Park it at [i][j] of this
         // team's buffer, then collect rows t*kSlice .. +kSlice-1 of ALL G tiles.
 #pragma unroll
@@ -186,7 +258,6 @@ polyt_gs_kernel(const __grid_constant__ CUtensorMap map_lo, const __grid_constan
         fence_proxy_async();
         group_sync();
         // ---- every buffer of the group is free: prefetch this team's next tile
-        const uint32_t next = poly + stride;
         if (j == 0 && next < prm.batch) {
             mbar_expect_tx(bar, kF_PolyBytes);
             tma_load_3d(buf, &map_lo, bar, 0, 0, (int) (next * G + t));
@@ -229,6 +300,7 @@ polyt_gs_kernel(const __grid_constant__ CUtensorMap map_lo, const __grid_constan
                 dst[tt * 4096 + ii * 64] = min(r - q, r);
             }
         }
+        }   // LOGG > 1
     }
     tmem_fence_before_sync();
     __syncthreads();
@@ -466,10 +538,10 @@ int tile_maps(CUtensorMap *lo, CUtensorMap *hi, const int32_t *base, size_t tile
 template <int LOGG>
 static int polyt_attrs() {
     const auto attr = cudaFuncAttributeMaxDynamicSharedMemorySize;
-    NTTB200_CUDA(cudaFuncSetAttribute(polyt_gs_kernel<LOGG, false, false>, attr, kY_SmemBytes));
-    NTTB200_CUDA(cudaFuncSetAttribute(polyt_gs_kernel<LOGG, true, false>, attr, kY_SmemBytes));
-    NTTB200_CUDA(cudaFuncSetAttribute(polyt_gs_kernel<LOGG, false, true>, attr, kY_SmemBytes));
-    NTTB200_CUDA(cudaFuncSetAttribute(polyt_gs_kernel<LOGG, true, true>, attr, kY_SmemBytes));
+    NTTB200_CUDA(cudaFuncSetAttribute(polyt_gs_kernel<LOGG, false, false>, attr, kY_SmemBytesCt));
+    NTTB200_CUDA(cudaFuncSetAttribute(polyt_gs_kernel<LOGG, true, false>, attr, kY_SmemBytesCt));
+    NTTB200_CUDA(cudaFuncSetAttribute(polyt_gs_kernel<LOGG, false, true>, attr, kY_SmemBytesCt));
+    NTTB200_CUDA(cudaFuncSetAttribute(polyt_gs_kernel<LOGG, true, true>, attr, kY_SmemBytesCt));
     NTTB200_CUDA(cudaFuncSetAttribute(polyt_ct_kernel<LOGG, false>, attr, kY_SmemBytesCt));
     NTTB200_CUDA(cudaFuncSetAttribute(polyt_ct_kernel<LOGG, true>, attr, kY_SmemBytesCt));
     return NTTB200_OK;
@@ -498,10 +570,10 @@ static void polyt_gs_launch(int grid, cudaStream_t st, const CUtensorMap &a_lo, 
                             const CUtensorMap &b_lo, const CUtensorMap &b_hi, const TileParams &tp,
                             const CrossTw &cross, bool l4) {
     if (l4) {
-        polyt_gs_kernel<LOGG, DUAL, true><<<grid, kM_Threads, kY_SmemBytes, st>>>(a_lo, a_hi, b_lo, b_hi,
+        polyt_gs_kernel<LOGG, DUAL, true><<<grid, kM_Threads, kY_SmemBytesCt, st>>>(a_lo, a_hi, b_lo, b_hi,
                                                                                   tp, cross);
     } else {
-        polyt_gs_kernel<LOGG, DUAL, false><<<grid, kM_Threads, kY_SmemBytes, st>>>(a_lo, a_hi, b_lo, b_hi,
+        polyt_gs_kernel<LOGG, DUAL, false><<<grid, kM_Threads, kY_SmemBytesCt, st>>>(a_lo, a_hi, b_lo, b_hi,
                                                                                    tp, cross);
     }
 }

@@ -461,7 +461,10 @@ int launch_tilecol_gs(nttb200_plan *p, const int32_t *d_in, const int32_t *d_b, 
     tp.lag = (uint32_t) ((lag_tiles >> logg) + 2);   // > one queue step (grid * 8 / G polynomials)
     // counters: one per polynomial + the error word, stream-ordered scratch
     uint32_t *ctr = nullptr;
-    NTTB200_CUDA(cudaMallocAsync(&ctr, sizeof(uint32_t) * (batch + 1), st));
+    {
+        int rca = scratch_alloc_async((void **) &ctr, sizeof(uint32_t) * (batch + 1), st);
+        if (rca != NTTB200_OK) return rca;
+    }
     NTTB200_CUDA(cudaMemsetAsync(ctr, 0, sizeof(uint32_t) * (batch + 1), st));
     tp.done = ctr;
     tp.error = ctr + batch;

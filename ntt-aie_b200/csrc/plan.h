@@ -85,6 +85,14 @@ int cuda_fail(cudaError_t e, const char *what);
 bool l4_enabled();
 inline bool use_l4(const nttb200_plan *p) { return p->q < (1u << 29) && l4_enabled(); }
 
+// Stream-ordered scratch (transform scratch of the multi-kernel products, the counters of the
+// persistent kernel) from a library-private memory pool of the CURRENT device that keeps its
+// pages across synchronisations (release threshold = max): with the default pool every
+// cudaDeviceSynchronize hands the pages back to the driver and the next call pays milliseconds
+// to map them again (measured: 8 ms on the first product after a synchronize at N = 2^13).
+// Freed with cudaFreeAsync; trimmed when the last plan of the process is destroyed.
+int scratch_alloc_async(void **p, size_t bytes, cudaStream_t st);
+
 // device-side table construction and input canonicalisation (tables.cu)
 int build_shoup_table(nttb200_plan *p, const int32_t *d_table);
 int build_generated_table(nttb200_plan *p, uint32_t kind, uint32_t base, uint32_t gen_logn,
