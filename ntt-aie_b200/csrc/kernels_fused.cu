@@ -331,11 +331,14 @@ static EncodeTiledFn encode_tiled() {
 // view of the batch for TMA: dim0 = 32 words of one half-row, dim1 = 64 rows
 // (stride 256 B), dim2 = polynomial (stride 16 KiB); box = one half of one polynomial
 // (general form: `rows` rows of 64 words per tile, rows*256 bytes per tile)
-int encode_tile_map(CUtensorMap *map, const int32_t *base, uint32_t rows, size_t batch) {
+// tile_stride_bytes = 0: tiles are contiguous; otherwise the distance between consecutive
+// tiles of this view (channel l of an RNS batch: L tiles apart)
+int encode_tile_map(CUtensorMap *map, const int32_t *base, uint32_t rows, size_t batch,
+                    size_t tile_stride_bytes) {
     EncodeTiledFn enc = encode_tiled();
     if (!enc) return NTTB200_ERR_CUDA;
     cuuint64_t dims[3] = {32, rows, (cuuint64_t) batch};
-    cuuint64_t strides[2] = {256, (cuuint64_t) rows * 256};
+    cuuint64_t strides[2] = {256, tile_stride_bytes ? (cuuint64_t) tile_stride_bytes : (cuuint64_t) rows * 256};
     cuuint32_t box[3] = {32, rows, 1};
     cuuint32_t estr[3] = {1, 1, 1};
     CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_INT32, 3, (void *) base, dims, strides, box, estr,
@@ -344,14 +347,22 @@ int encode_tile_map(CUtensorMap *map, const int32_t *base, uint32_t rows, size_t
     return r == CUDA_SUCCESS ? NTTB200_OK : NTTB200_ERR_CUDA;
 }
 
-static int make_half_map(CUtensorMap *map, const int32_t *base, size_t batch) {
-    return encode_tile_map(map, base, 64, batch);
+static int make_half_map(CUtensorMap *map, const int32_t *base, size_t batch, size_t tile_stride_bytes = 0) {
+    return encode_tile_map(map, base, 64, batch, tile_stride_bytes);
 }
 
 // both half-tile maps of a buffer of `tiles` contiguous 4096-word tiles
 int tile_maps(CUtensorMap *lo, CUtensorMap *hi, const int32_t *base, size_t tiles) {
     int rc = make_half_map(lo, base, tiles);
     if (rc == NTTB200_OK) rc = make_half_map(hi, base + 32, tiles);
+    return rc;
+}
+// every tile_mul-th tile starting at base: `tiles` tiles, tile_mul * 16 KiB apart
+int tile_maps_strided(CUtensorMap *lo, CUtensorMap *hi, const int32_t *base, size_t tiles,
+                      uint32_t tile_mul) {
+    const size_t stride = (size_t) tile_mul * kF_PolyBytes;
+    int rc = make_half_map(lo, base, tiles, stride);
+    if (rc == NTTB200_OK) rc = make_half_map(hi, base + 32, tiles, stride);
     return rc;
 }
 

@@ -48,8 +48,8 @@ struct PolymulParams {
     uint32_t scale;        // N^-1 * 2^32 mod q and its Shoup companion
     uint32_t scale_shoup;
     uint32_t four_q;       // opaque 4q for the 4q-lazy butterflies (q < 2^29)
-    uint32_t tile_mul;     // product p lives in tile p * tile_mul + tile_off of all three buffers:
-    uint32_t tile_off;     // (1, 0) for plain batches, (L, l) for channel l of an RNS batch
+    uint32_t out_words;    // distance between consecutive products in `out`: 4096, or L * 4096 for one
+                           // channel of an RNS batch (the operand views are strided by their tensor maps)
 };
 
 // CT stage K on registers pairing rows i and i + 2^K of one column, uniform twiddles
@@ -153,8 +153,8 @@ polymul4096_kernel(const __grid_constant__ CUtensorMap a_lo, const __grid_consta
     uint32_t parity = 0;
     if (j == 0 && poly < prm.batch) {
         mbar_expect_tx(bar, kF_PolyBytes);
-        tma_load_3d(buf, &a_lo, bar, 0, 0, (int) (poly * prm.tile_mul + prm.tile_off));
-        tma_load_3d(buf + kF_PolyBytes / 2, &a_hi, bar, 0, 0, (int) (poly * prm.tile_mul + prm.tile_off));
+        tma_load_3d(buf, &a_lo, bar, 0, 0, (int) poly);
+        tma_load_3d(buf + kF_PolyBytes / 2, &a_hi, bar, 0, 0, (int) poly);
     }
     // buffer layout as TMA writes it: two halves of [64 rows][32 words], 128 B swizzle
     const uint32_t r1_row = buf + j * 128;
@@ -217,8 +217,8 @@ polymul4096_kernel(const __grid_constant__ CUtensorMap a_lo, const __grid_consta
                 sync();
                 if (j == 0) {
                     mbar_expect_tx(bar, kF_PolyBytes);
-                    tma_load_3d(buf, &b_lo, bar, 0, 0, (int) (poly * prm.tile_mul + prm.tile_off));
-                    tma_load_3d(buf + kF_PolyBytes / 2, &b_hi, bar, 0, 0, (int) (poly * prm.tile_mul + prm.tile_off));
+                    tma_load_3d(buf, &b_lo, bar, 0, 0, (int) poly);
+                    tma_load_3d(buf + kF_PolyBytes / 2, &b_hi, bar, 0, 0, (int) poly);
                 }
             }
             // ---- rows: CT stages 5..0, private twiddles from tensor memory
@@ -278,8 +278,8 @@ polymul4096_kernel(const __grid_constant__ CUtensorMap a_lo, const __grid_consta
         const uint32_t next = poly + stride;
         if (j == 0 && next < prm.batch) {
             mbar_expect_tx(bar, kF_PolyBytes);
-            tma_load_3d(buf, &a_lo, bar, 0, 0, (int) (next * prm.tile_mul + prm.tile_off));
-            tma_load_3d(buf + kF_PolyBytes / 2, &a_hi, bar, 0, 0, (int) (next * prm.tile_mul + prm.tile_off));
+            tma_load_3d(buf, &a_lo, bar, 0, 0, (int) next);
+            tma_load_3d(buf + kF_PolyBytes / 2, &a_hi, bar, 0, 0, (int) next);
         }
         // ---- GS stages 6..11 (uniform twiddles), N^-1 * 2^32 at the store
         if (L4) {   // the N^-1 multiplication below accepts any word: no canonicalisation
@@ -297,7 +297,7 @@ polymul4096_kernel(const __grid_constant__ CUtensorMap a_lo, const __grid_consta
             pm_gs_uniform<4, false>(v, uni_inv, q, two_q, zero);
             pm_gs_uniform<5, true>(v, uni_inv, q, two_q, zero);
         }
-        uint32_t *dst = prm.out + ((size_t) poly * prm.tile_mul + prm.tile_off) * 4096 + j;
+        uint32_t *dst = prm.out + (size_t) poly * prm.out_words + j;
 #pragma unroll
         for (int i = 0; i < 64; i++) {
             const uint32_t r = shoup_mul_lazy(v[i], prm.scale, prm.scale_shoup, q);
@@ -311,6 +311,7 @@ polymul4096_kernel(const __grid_constant__ CUtensorMap a_lo, const __grid_consta
 
 // --------------------------------------------------------------------- host side
 int tile_maps(CUtensorMap *lo, CUtensorMap *hi, const int32_t *base, size_t tiles);  // kernels_fused.cu
+int tile_maps_strided(CUtensorMap *lo, CUtensorMap *hi, const int32_t *base, size_t tiles, uint32_t tile_mul);
 
 int polymul_prepare() {
     const auto attr = cudaFuncAttributeMaxDynamicSharedMemorySize;
@@ -352,12 +353,12 @@ int launch_polymul4096_strided(nttb200_plan *fwd, nttb200_plan *inv, const int32
         return NTTB200_ERR_UNSUPPORTED;
     }
     CUtensorMap a_lo, a_hi, b_lo, b_hi;
-    if (tile_maps(&a_lo, &a_hi, d_a, batch * tile_mul) != NTTB200_OK ||
-        tile_maps(&b_lo, &b_hi, d_b, batch * tile_mul) != NTTB200_OK) {
+    if (tile_maps_strided(&a_lo, &a_hi, d_a + (size_t) tile_off * 4096, batch, tile_mul) != NTTB200_OK ||
+        tile_maps_strided(&b_lo, &b_hi, d_b + (size_t) tile_off * 4096, batch, tile_mul) != NTTB200_OK) {
         return NTTB200_ERR_UNSUPPORTED;
     }
     PolymulParams prm;
-    prm.out = reinterpret_cast<uint32_t *>(d_c);
+    prm.out = reinterpret_cast<uint32_t *>(d_c) + (size_t) tile_off * 4096;
     prm.tw_fwd = fwd->d_tw_r1;
     prm.tw_inv = inv->d_tw_r1;
     prm.batch = (uint32_t) batch;
@@ -368,8 +369,7 @@ int launch_polymul4096_strided(nttb200_plan *fwd, nttb200_plan *inv, const int32
     prm.scale = (uint32_t) sc;
     prm.scale_shoup = (uint32_t) ((sc << 32) / inv->q);
     prm.four_q = 4u * fwd->q;
-    prm.tile_mul = tile_mul;
-    prm.tile_off = tile_off;
+    prm.out_words = tile_mul * 4096u;
     const uint64_t ctas = (batch + kP_Teams - 1) / kP_Teams;
     const int grid = (int) (ctas < (uint64_t) fwd->sm_count ? ctas : (uint64_t) fwd->sm_count);
     static const int lockstep = []() {

@@ -465,7 +465,8 @@ fused_ct_small_kernel(const __grid_constant__ CUtensorMap map_lo,
 }
 
 // --------------------------------------------------------------------- host side
-int encode_tile_map(CUtensorMap *map, const int32_t *base, uint32_t rows, size_t blocks);  // kernels_fused.cu
+int encode_tile_map(CUtensorMap *map, const int32_t *base, uint32_t rows, size_t blocks,
+                    size_t tile_stride_bytes = 0);  // kernels_fused.cu
 
 template <int LOGN>
 static int small_set_attr() {
