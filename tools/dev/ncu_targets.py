@@ -1,6 +1,6 @@
 """Launch each kernel family a few times (for `ncu -k regex:<name>` captures):
     python tools/dev/ncu_targets.py <which>
-which: headline | polymul | poly15 | tilecol16 | ct4096 | fourstep_local"""
+which: headline | polymul | poly15 | tilecol16 | ct4096 | ct15 | fourstep_local"""
 import os, sys, torch
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 import ntt_aie_b200 as nt
@@ -37,5 +37,7 @@ elif which == "tilecol16":
     run(16, 28, "gs")
 elif which == "ct4096":
     run(12, 28, "ct")
+elif which == "ct15":
+    run(15, 26, "ct")
 elif which == "fourstep_local":
     run(23, 23, "gs")

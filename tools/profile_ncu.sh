@@ -20,5 +20,6 @@ cap headline fused_gs4096 fused_gs4096
 cap polymul polymul4096 polymul4096
 cap poly15 polyt_gs polyt_gs15
 cap tilecol16 tilecol_gs tilecol_gs16
-cap ct4096 tile_ct_db tile_ct_db
+cap ct4096 tile_ct_h tile_ct_h
+cap ct15 polyt_ct polyt_ct15
 ls -la gpurun_out/*.ncu-rep gpurun_out/launches_bench.csv
