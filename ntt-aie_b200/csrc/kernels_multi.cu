@@ -394,7 +394,10 @@ poly_gs_kernel(const __grid_constant__ CUtensorMap map_lo, const __grid_constant
 // buffer (an already transformed operand) before it is stored -- a Montgomery product
 // x*y*2^-32, canonical.  That operand's TMA load is issued as soon as the rows are in
 // registers and lands behind the six row stages, so it costs no waiting.
-template <bool RNS, bool SMEM_TW = false, bool MULT = false>
+// STAGED (not with SMEM_TW / MULT): an 8 KiB staging slot per team takes the output in two
+// halves (see tile_ct_h_kernel below), so the tile buffer receives the prefetch of the team's next
+// tile as soon as the rows are in registers instead of after the store has drained.
+template <bool RNS, bool SMEM_TW = false, bool MULT = false, bool STAGED = false>
 __global__ void __launch_bounds__(kM_Threads, 1)
 tile_ct_kernel(const __grid_constant__ CUtensorMap map_lo, const __grid_constant__ CUtensorMap map_hi,
                const __grid_constant__ CUtensorMap out_lo, const __grid_constant__ CUtensorMap out_hi,
@@ -413,6 +416,9 @@ tile_ct_kernel(const __grid_constant__ CUtensorMap map_lo, const __grid_constant
     const uint32_t zero = prm.zero;
 
     const uint32_t tws = bar_base + 64;
+    static_assert(!STAGED || (!SMEM_TW && !MULT), "the staged variant has no table / product form");
+    const uint32_t stg = ((bar_base + 64 + 1023u) & ~1023u) + team * (kF_PolyBytes / 2);
+    const uint32_t st_row = stg + j * 128;
     if (SMEM_TW) {
         for (int i = tid; i < kM_TwTile; i += kM_Threads) {
             uint4 x = __ldg(prm.tw_tile + i);
@@ -496,6 +502,61 @@ tile_ct_kernel(const __grid_constant__ CUtensorMap map_lo, const __grid_constant
                 tma_load_3d(buf + kF_PolyBytes / 2, &mul_hi, bar, 0, 0, (int) tile_cur);
             }
         }
+        if constexpr (STAGED) {
+            // ---- the tile buffer is free: prefetch the team's next tile; the staging slot is free
+            // once the previous tile's right half has been read by its store
+            fence_proxy_async();
+            if (j == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+            team_sync(team);
+            const uint32_t next = u + kM_Teams;
+            uint32_t tile_next = 0;
+            if (next < u_end) tile_next = tile_of(next, c_cur);
+            if (j == 0 && next < u_end) {
+                mbar_expect_tx(bar, kF_PolyBytes);
+                tma_load_3d(buf, &map_lo, bar, 0, 0, (int) tile_next);
+                tma_load_3d(buf + kF_PolyBytes / 2, &map_hi, bar, 0, 0, (int) tile_next);
+            }
+            // ---- rows: stage 5 pairs the halves, stages 4..0 run per half
+            const TwGlobal twr{tw + j};
+            ct_stage_t<5, true>(v, twr, q, two_q, zero);
+#pragma unroll
+            for (int h = 0; h < 2; h++) {
+                if (h == 0) {
+                    ct_half_stage<4, 0, -1>(v, twr, q, two_q, 0u, zero);
+                    ct_half_stage<3, 0, -1>(v, twr, q, two_q, 0u, zero);
+                    ct_half_stage<2, 0, -1>(v, twr, q, two_q, 0u, zero);
+                    ct_half_stage<1, 0, -1>(v, twr, q, two_q, 0u, zero);
+                    ct_half_stage<0, 0, -1>(v, twr, q, two_q, 0u, zero);
+                } else {
+                    ct_half_stage<4, 1, -1>(v, twr, q, two_q, 0u, zero);
+                    ct_half_stage<3, 1, -1>(v, twr, q, two_q, 0u, zero);
+                    ct_half_stage<2, 1, -1>(v, twr, q, two_q, 0u, zero);
+                    ct_half_stage<1, 1, -1>(v, twr, q, two_q, 0u, zero);
+                    ct_half_stage<0, 1, -1>(v, twr, q, two_q, 0u, zero);
+                    if (j == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+                    team_sync(team);
+                }
+#pragma unroll
+                for (int c = 0; c < 8; c++) {
+                    uint32_t o[4];
+#pragma unroll
+                    for (int e = 0; e < 4; e++) {
+                        uint32_t r = v[32 * h + 4 * c + e];
+                        r = min(r - two_q, r);
+                        o[e] = min(r - q, r);
+                    }
+                    sts128(st_row + ((c << 4) ^ r1_xor), o[0], o[1], o[2], o[3]);
+                }
+                fence_proxy_async();
+                team_sync(team);
+                if (j == 0) {
+                    tma_store_3d(h == 0 ? &out_lo : &out_hi, stg, 0, 0, (int) tile_cur);
+                    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+                }
+            }
+            tile_cur = tile_next;
+            continue;
+        }
         // ---- rows: stages 5..0
         if (SMEM_TW) {
             ct_round<true>(v, TwShared{tws + j * 16}, q, two_q, zero);
@@ -547,6 +608,7 @@ tile_ct_kernel(const __grid_constant__ CUtensorMap map_lo, const __grid_constant
         }
         tile_cur = tile_next;
     }
+    if (STAGED && j == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
     // every store was followed by wait_group.read, so shared memory is no longer in
     // use when the CTA exits; the writes themselves complete before the grid does.
     // (A trailing divergent wait here also stops ptxas from keeping q/2q in uniform
@@ -1137,6 +1199,11 @@ column_kernel(const uint32_t *__restrict__ in, uint32_t *__restrict__ out,
 int tile_maps(CUtensorMap *lo, CUtensorMap *hi, const int32_t *base, size_t tiles);  // kernels_fused.cu
 
 static const RnsConsts kNoRns{};
+constexpr int kM_SmemBytesStaged = kM_SmemBytes + kM_Teams * (kF_PolyBytes / 2) + 1024;
+static bool ct_staged() {   // NTTB200_CT_UNSTAGED=1: the first version (A/B)
+    static const bool on = getenv("NTTB200_CT_UNSTAGED") == nullptr;
+    return on;
+}
 
 int multi_set_attrs() {
     const auto attr = cudaFuncAttributeMaxDynamicSharedMemorySize;
@@ -1146,6 +1213,8 @@ int multi_set_attrs() {
     NTTB200_CUDA(cudaFuncSetAttribute(tile_gs_kernel<true, true>, attr, kM_SmemBytes));
     NTTB200_CUDA(cudaFuncSetAttribute(tile_ct_kernel<false>, attr, kM_SmemBytes));
     NTTB200_CUDA(cudaFuncSetAttribute(tile_ct_kernel<true>, attr, kM_SmemBytes));
+    NTTB200_CUDA(cudaFuncSetAttribute(tile_ct_kernel<false, false, false, true>, attr, kM_SmemBytesStaged));
+    NTTB200_CUDA(cudaFuncSetAttribute(tile_ct_kernel<true, false, false, true>, attr, kM_SmemBytesStaged));
     NTTB200_CUDA(cudaFuncSetAttribute(tile_gs_kernel<false, false, 1>, attr, kM_SmemBytesTw));
     NTTB200_CUDA(cudaFuncSetAttribute(tile_gs_kernel<false, false, 2>, attr, kM_SmemBytesTw));
     NTTB200_CUDA(cudaFuncSetAttribute(tile_gs_kernel<true, false, 2>, attr, kM_SmemBytesTw));
@@ -1626,6 +1695,9 @@ int launch_multi_ct_mul(nttb200_plan *p, const int32_t *d_in, const int32_t *d_m
             tile_ct_kernel<false, true><<<tile_grid(p, tiles), kM_Threads, kM_SmemBytesTw, st>>>(
                 in_lo, in_hi, out_lo, out_hi, tp, kNoRns, in_lo, in_hi);
         }
+    } else if (ct_staged()) {
+        tile_ct_kernel<false, false, false, true><<<tile_grid(p, tiles), kM_Threads, kM_SmemBytesStaged, st>>>(
+            in_lo, in_hi, out_lo, out_hi, tp, kNoRns, in_lo, in_hi);
     } else {
         tile_ct_kernel<false><<<tile_grid(p, tiles), kM_Threads, kM_SmemBytes, st>>>(
             in_lo, in_hi, out_lo, out_hi, tp, kNoRns, in_lo, in_hi);
@@ -1676,8 +1748,13 @@ int rns_launch(int sm_count, int kind, const uint4 *d_tw_tile, const uint4 *h_po
         }
     } else if (kind == 1) {  // CT (output tensor maps on d_out)
         if (tile_maps(&b_lo, &b_hi, d_out, (size_t) tiles) != NTTB200_OK) return NTTB200_ERR_CUDA;
-        tile_ct_kernel<true><<<grid, kM_Threads, kM_SmemBytes, st>>>(a_lo, a_hi, b_lo, b_hi, tp, rc, a_lo,
-                                                                     a_hi);
+        if (ct_staged()) {
+            tile_ct_kernel<true, false, false, true><<<grid, kM_Threads, kM_SmemBytesStaged, st>>>(
+                a_lo, a_hi, b_lo, b_hi, tp, rc, a_lo, a_hi);
+        } else {
+            tile_ct_kernel<true><<<grid, kM_Threads, kM_SmemBytes, st>>>(a_lo, a_hi, b_lo, b_hi, tp, rc, a_lo,
+                                                                         a_hi);
+        }
     } else {                 // GS of the pointwise product, scaled
         if (tile_maps(&b_lo, &b_hi, d_b, (size_t) tiles) != NTTB200_OK) return NTTB200_ERR_CUDA;
         if (seg_tables(batch)) {
