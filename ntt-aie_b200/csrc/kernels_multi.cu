@@ -1471,7 +1471,9 @@ int launch_multi_gs(nttb200_plan *p, const int32_t *d_in, int32_t *d_out, size_t
     // pass writes is still in the 126 MB L2 when the column pass reads it, so the
     // intermediate never costs HBM bandwidth.
     {
-        int rc = launch_tilecol_gs(p, d_in, nullptr, d_out, batch, st);
+        int rc = launch_polyc_gs(p, d_in, nullptr, d_out, batch, st);   // opt-in (NTTB200_CLUSTER16)
+        if (rc != NTTB200_ERR_UNSUPPORTED) return rc;
+        rc = launch_tilecol_gs(p, d_in, nullptr, d_out, batch, st);
         if (rc != NTTB200_ERR_UNSUPPORTED) return rc;
         rc = launch_polyt_gs(p, d_in, nullptr, d_out, batch, st);
         if (rc != NTTB200_ERR_UNSUPPORTED) return rc;
@@ -1568,7 +1570,9 @@ int launch_multi_gs_dual(nttb200_plan *p, const int32_t *d_a, const int32_t *d_b
         return NTTB200_ERR_UNSUPPORTED;
     }
     if (batch == 0) return NTTB200_OK;
-    int rc = launch_tilecol_gs(p, d_a, d_b, d_out, batch, st);
+    int rc = launch_polyc_gs(p, d_a, d_b, d_out, batch, st);   // opt-in (NTTB200_CLUSTER16)
+    if (rc != NTTB200_ERR_UNSUPPORTED) return rc;
+    rc = launch_tilecol_gs(p, d_a, d_b, d_out, batch, st);
     if (rc != NTTB200_ERR_UNSUPPORTED) return rc;
     rc = launch_polyt_gs(p, d_a, d_b, d_out, batch, st);
     if (rc != NTTB200_ERR_UNSUPPORTED) return rc;

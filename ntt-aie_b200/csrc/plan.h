@@ -110,6 +110,8 @@ int launch_polyt_gs(nttb200_plan *p, const int32_t *d_in, const int32_t *d_b, in
                     size_t batch, cudaStream_t st);
 int launch_polyt_ct(nttb200_plan *p, const int32_t *d_in, int32_t *d_out, size_t batch,
                     cudaStream_t st);
+int launch_polyc_gs(nttb200_plan *p, const int32_t *d_in, const int32_t *d_b, int32_t *d_out,
+                    size_t batch, cudaStream_t st);
 
 // N = 2^13..2^16 as one persistent kernel of tile items and column items (kernels_tilecol.cu)
 int tilecol_prepare();
