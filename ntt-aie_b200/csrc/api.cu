@@ -657,9 +657,9 @@ int nttb200_polymul_negacyclic(nttb200_plan *fwd, nttb200_plan *inv, const int32
         // NTT(a), NTT(b) into scratch; pointwise product, inverse transform and the
         // N^-1 scaling in one pass over them
         {
-        int rca = scratch_alloc_async((void **) &tmp, sizeof(int32_t) * words * 2, st);
-        if (rca != NTTB200_OK) return rca;
-    }
+            int rca = scratch_alloc_async((void **) &tmp, sizeof(int32_t) * words * 2, st);
+            if (rca != NTTB200_OK) return rca;
+        }
         int rc = launch_multi_ct(fwd, d_a, tmp, batch, st);
         if (rc == NTTB200_OK && fwd->logn == 12 && inv->d_tw_r1 && !getenv("NTTB200_POLYMUL_DUAL")) {
             // N = 4096: the pointwise product rides on the second forward transform (its
@@ -681,9 +681,9 @@ int nttb200_polymul_negacyclic(nttb200_plan *fwd, nttb200_plan *inv, const int32
         fwd->d_tw_r1 && inv->d_tw_r1 && batch % ((size_t) 2048 >> fwd->logn) == 0) {
         // N = 512..2048: warp-per-block CT, CT, then pointwise + inverse + scaling in one kernel
         {
-        int rca = scratch_alloc_async((void **) &tmp, sizeof(int32_t) * words * 2, st);
-        if (rca != NTTB200_OK) return rca;
-    }
+            int rca = scratch_alloc_async((void **) &tmp, sizeof(int32_t) * words * 2, st);
+            if (rca != NTTB200_OK) return rca;
+        }
         size_t done = 0;
         int rc = launch_small(fwd, 3, d_a, nullptr, tmp, batch, st, &done);
         if (rc == NTTB200_OK) rc = launch_small(fwd, 3, d_b, nullptr, tmp + words, batch, st, &done);
