@@ -1608,6 +1608,8 @@ int launch_multi_ct_mul(nttb200_plan *p, const int32_t *d_in, const int32_t *d_m
         // 65,536 tiles against 0.516 ms for the double-buffered TMA-store kernel below)
         int rc = launch_polyt_ct(p, d_in, d_out, batch, st);
         if (rc != NTTB200_ERR_UNSUPPORTED) return rc;
+        rc = launch_tilecol_ct(p, d_in, d_out, batch, st);
+        if (rc != NTTB200_ERR_UNSUPPORTED) return rc;
     }
     if (logg >= 1 && logg <= 3 && poly_kernel_enabled()) {
         // N = 2^13..2^15: one pass, cross-tile stages inside the CTA

@@ -353,6 +353,295 @@ tilecol_gs_kernel(const __grid_constant__ CUtensorMap map_lo, const __grid_const
     if (warp == 0) tmem_dealloc_512(tmem_base);
 }
 
+// ------------------------------------------------------------ CT (forward partner)
+// The same two item kinds in the opposite order: C-items first (the 1/16 slice of all 16
+// tiles of a polynomial straight from the input: 16 x 128-bit loads, the four cross-tile
+// stages 15..12, 16 x 128-bit stores of the LAZY intermediate into `out`), T-items trail by
+// `lag` polynomials (the tile comes back from L2 by TMA once all 16 C-items of its polynomial
+// have published; columns, exchange, rows, output in two halves through the staging slot as
+// in tile_ct_h_kernel).  The TMA load reads what other SMs wrote with ordinary stores: the
+// writers' fence.acq_rel.gpu puts the data in L2 before the counter moves, the reader orders
+// its async-proxy load behind the counter read with fence.proxy.async.
+constexpr int kTC_StageBase = kM_Teams * kF_PolyBytes + 128 + 8 * 512;
+constexpr int kTC_SmemBytesCt = ((kTC_StageBase + 1023) / 1024) * 1024 + kM_Teams * (kF_PolyBytes / 2) + 1024;
+
+template <int S, int B0, int NB, int BIN, bool L4>
+__device__ __forceinline__ void tc_ct_blocks(uint32_t (&v)[64], const uint32_t *t, uint32_t q,
+                                             uint32_t two_q, uint32_t four_q, uint32_t zero) {
+    if (L4) {
+        ct_blocks_l4<S, B0, NB, BIN>(v, t, q, two_q, four_q, zero);
+    } else {
+        ct_blocks<S, B0, NB, true>(v, t, q, two_q, zero);
+    }
+}
+template <int H, int B4, bool L4>
+__device__ __forceinline__ void tc_ct_half(uint32_t (&v)[64], uint32_t taddr, const uint32_t *ts2,
+                                           const uint32_t *ts345, uint32_t q, uint32_t two_q,
+                                           uint32_t four_q, uint32_t zero) {
+    constexpr int B3 = ct_l4_out(B4), B2 = ct_l4_out(B3), B1 = ct_l4_out(B2), B0 = ct_l4_out(B1);
+    uint32_t ta[16], tb[16];
+    tmem_ld16(taddr + 64 + 16 * H, ta);
+    tc_ct_blocks<4, H, 1, B4, L4>(v, ts345 + 8 + 2 * H, q, two_q, four_q, zero);
+    tc_ct_blocks<3, 2 * H, 2, B3, L4>(v, ts345 + 4 * H, q, two_q, four_q, zero);
+    tc_ct_blocks<2, 4 * H, 4, B2, L4>(v, ts2 + 8 * H, q, two_q, four_q, zero);
+    tmem_wait_ld16(ta);
+    tmem_ld16(taddr + 32 * H + 16, tb);
+    tc_ct_blocks<1, 8 * H, 8, B1, L4>(v, ta, q, two_q, four_q, zero);
+    tmem_wait_ld16(tb);
+    tmem_ld16(taddr + 32 * H, ta);
+    tc_ct_blocks<0, 16 * H + 8, 8, B0, L4>(v, tb, q, two_q, four_q, zero);
+    tmem_wait_ld16(ta);
+    tc_ct_blocks<0, 16 * H, 8, B0, L4>(v, ta, q, two_q, four_q, zero);
+}
+
+template <bool L4>
+__global__ void __launch_bounds__(kM_Threads, 1)
+tilecol_ct_kernel(const uint32_t *__restrict__ in, const __grid_constant__ CUtensorMap mid_lo,
+                  const __grid_constant__ CUtensorMap mid_hi, const __grid_constant__ CUtensorMap out_lo,
+                  const __grid_constant__ CUtensorMap out_hi, const TileColParams prm,
+                  const __grid_constant__ CrossTw cross) {
+    constexpr int LOGG = 4, G = 16, H = 2, K = G / (2 * H);
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t data_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    const uint32_t bar_base = data_base + kM_Teams * kF_PolyBytes;
+    const uint32_t tmem_slot = bar_base + 64, r2base = bar_base + 128;
+    const uint32_t stage_base = (data_base + kTC_StageBase + 1023u) & ~1023u;
+    const int tid = threadIdx.x;
+    const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);
+    const int team = warp >> 1;
+    const int j = tid & 63;
+    const uint32_t q = prm.q, two_q = 2u * prm.q, four_q = prm.four_q, zero = prm.zero;
+    const uint32_t cta_half = blockIdx.x & (H - 1);
+    const uint32_t parity_h = team & 1;
+
+    // ---- prologue: TMEM, mbarriers, this CTA's position tables (as in the GS kernel)
+    if (warp == 0) tmem_alloc_512(tmem_slot);
+    if (tid < kM_Teams) mbar_init(bar_base + tid * 8, 1);
+    for (int i = tid; i < (G / H) * 32; i += kM_Threads) {
+        const uint32_t pos = cta_half * 8 + (i >> 5);
+        const uint4 x = __ldg(prm.tw_tile + (size_t) pos * kM_TwTile + (i & 31) * kM_TwRow + 64);
+        sts128(r2base + i * 16, x.x, x.y, x.z, x.w);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    tmem_fence_before_sync();
+    __syncthreads();
+    tmem_fence_after_sync();
+    const uint32_t tmem_base = lds32(tmem_slot);
+    const uint32_t lane_base = tmem_base + ((uint32_t) (warp & 3) << 21);
+    {
+        const uint32_t h = (uint32_t) (warp & 3) >> 1;
+#pragma unroll 1
+        for (int k = 0; k < K; k++) {
+            const uint32_t pos = cta_half * 8 + 2 * k + h;
+            tmem_fill_table(lane_base + (uint32_t) k * 128u, prm.tw_tile + (size_t) pos * kM_TwTile + j,
+                            kM_TwRow, warp);
+        }
+        tmem_wait_st();
+    }
+    tmem_fence_before_sync();
+    __syncthreads();
+    tmem_fence_after_sync();
+
+    // ---- this team's two work queues
+    const uint32_t class_teams = (gridDim.x / H) * (kM_Teams / 2);
+    const uint32_t t_total = prm.batch * K;
+    uint32_t tq = (blockIdx.x / H) * (kM_Teams / 2) + (team >> 1);
+    const uint32_t num_teams = gridDim.x * kM_Teams;
+    const uint32_t c_total = prm.batch * G;
+    uint32_t cq = blockIdx.x * kM_Teams + team;
+
+    const uint32_t buf = data_base + team * kF_PolyBytes;
+    const uint32_t stg = stage_base + team * (kF_PolyBytes / 2);
+    const uint32_t bar = bar_base + team * 8;
+    uint32_t parity = 0;
+    const uint32_t r1_row = buf + j * 128;
+    const uint32_t st_row = stg + j * 128;
+    const uint32_t r1_xor = (j & 7) << 4;
+    const uint32_t r2_col = buf + (j >> 5) * (kF_PolyBytes / 2) + (j & 3) * 4;
+    const uint32_t r2_chunk = ((j & 31) >> 2) << 4;
+
+    auto tile_index = [&](uint32_t i) -> uint32_t {
+        const uint32_t p = i / K, k = i - p * K;
+        return p * G + cta_half * 8 + 2 * k + parity_h;
+    };
+    // thread j == 0 of the team: load T-item i's tile if its polynomial is complete
+    bool loaded = false;     // meaningful in thread j == 0 only
+    auto try_load = [&](uint32_t i, bool must) {
+        if (j != 0 || loaded || i >= t_total) return;
+        const uint32_t p = i / K;
+        uint32_t spins = 0;
+        while (ld_counter(prm.done + p) < 2 * G) {
+            if (!must) return;
+            __nanosleep(64);
+            if (++spins > kTC_SpinLimit) {
+                atomicExch(prm.error, 1u);
+                break;
+            }
+        }
+        asm volatile("fence.proxy.async;" ::: "memory");
+        const int tile = (int) tile_index(i);
+        mbar_expect_tx(bar, kF_PolyBytes);
+        tma_load_3d(buf, &mid_lo, bar, 0, 0, tile);
+        tma_load_3d(buf + kF_PolyBytes / 2, &mid_hi, bar, 0, 0, tile);
+        loaded = true;
+    };
+    uint32_t pending = 0xffffffffu;
+    auto publish = [&]() {
+        if (pending != 0xffffffffu) {
+            __syncwarp();
+            if ((tid & 31) == 0) {
+                asm volatile("fence.acq_rel.gpu;" ::: "memory");
+                asm volatile("red.relaxed.gpu.global.add.u32 [%0], 1;" ::"l"(prm.done + pending) : "memory");
+            }
+            pending = 0xffffffffu;
+        }
+    };
+    // 4q-lazy bounds: after the cross-tile stages, after the columns, at row stage 4, at the end
+    constexpr int kB1 = ct_l4_out_n(1, LOGG), kB2 = ct_l4_out_n(kB1, 6), kB4 = ct_l4_out(kB2),
+                  kB3 = ct_l4_out_n(kB4, 5);
+
+    while (cq < c_total || tq < t_total) {
+        const bool c_left = cq < c_total;
+        const uint32_t c_poly = c_left ? cq / G : 0;
+        // ---- T-items whose polynomial trails this team's next C-item by at least `lag`, or any
+        // T-item once the C-items are exhausted
+        while (tq < t_total && (!c_left || tq / K + prm.lag <= c_poly)) {
+            if (!c_left) publish();          // nothing of this team may stay unpublished while it waits
+            const uint32_t k = tq - (tq / K) * K;
+            const uint32_t tile_cur = tile_index(tq);
+            const uint32_t tw1 = lane_base + k * 128u;
+            const Tw16c tw2{r2base + (2 * k + parity_h) * 512u};
+            try_load(tq, true);
+            uint32_t v[64];
+            mbar_wait(bar, parity);
+            parity ^= 1;
+            loaded = false;
+#pragma unroll
+            for (int i = 0; i < 64; i++) {
+                v[i] = lds32(r2_col + i * 128 + (r2_chunk ^ ((i & 7) << 4)));
+            }
+            if (L4) {
+                ct_round_l4<kB1>(v, tw2, q, two_q, four_q, zero);
+            } else {
+                ct_round<true>(v, tw2, q, two_q, zero);
+            }
+#pragma unroll
+            for (int i = 0; i < 64; i++) {
+                asm volatile("st.shared.u32 [%0], %1;" ::"r"(r2_col + i * 128 + (r2_chunk ^ ((i & 7) << 4))),
+                             "r"(v[i])
+                             : "memory");
+            }
+            team_sync(team);
+#pragma unroll
+            for (int c = 0; c < 16; c++) {
+                uint4 x = lds128(r1_row + (c >> 3) * (kF_PolyBytes / 2) + (((c & 7) << 4) ^ r1_xor));
+                v[4 * c + 0] = x.x;
+                v[4 * c + 1] = x.y;
+                v[4 * c + 2] = x.z;
+                v[4 * c + 3] = x.w;
+            }
+            // the tile buffer is free: the next T-item's tile if its polynomial is already complete
+            fence_proxy_async();
+            if (j == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+            team_sync(team);
+            tq += class_teams;
+            try_load(tq, false);
+            publish();
+            uint32_t ts345[16], ts2[16];
+            tmem_ld16(tw1 + 112, ts345);
+            tmem_wait_ld16(ts345);
+            tmem_ld16(tw1 + 96, ts2);
+            tc_ct_blocks<5, 0, 1, kB2, L4>(v, ts345 + 12, q, two_q, four_q, zero);
+            tmem_wait_ld16(ts2);
+#pragma unroll
+            for (int h = 0; h < 2; h++) {
+                if (h == 0) {
+                    tc_ct_half<0, kB4, L4>(v, tw1, ts2, ts345, q, two_q, four_q, zero);
+                } else {
+                    tc_ct_half<1, kB4, L4>(v, tw1, ts2, ts345, q, two_q, four_q, zero);
+                    if (j == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+                    team_sync(team);
+                }
+#pragma unroll
+                for (int c = 0; c < 8; c++) {
+                    uint32_t o[4];
+#pragma unroll
+                    for (int e = 0; e < 4; e++) {
+                        uint32_t r = v[32 * h + 4 * c + e];
+                        if (L4) {
+                            o[e] = canon_l4(kB3, r, q, two_q, four_q);
+                        } else {
+                            r = min(r - two_q, r);
+                            o[e] = min(r - q, r);
+                        }
+                    }
+                    sts128(st_row + ((c << 4) ^ r1_xor), o[0], o[1], o[2], o[3]);
+                }
+                fence_proxy_async();
+                team_sync(team);
+                if (j == 0) {
+                    tma_store_3d(h == 0 ? &out_lo : &out_hi, stg, 0, 0, (int) tile_cur);
+                    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+                }
+            }
+        }
+        if (!c_left) continue;
+
+        // ---- C-item: the cross-tile stages of one slice of polynomial p
+        publish();
+        const uint32_t p = cq / G, k = cq - p * G;
+        const size_t off = ((size_t) p << (12 + LOGG)) + k * (4096 / G) + 4 * j;
+        uint32_t w[64];
+#pragma unroll
+        for (int tt = 0; tt < G; tt++) {
+            uint4 x;
+            asm volatile("ld.global.L1::no_allocate.v4.u32 {%0, %1, %2, %3}, [%4];"
+                         : "=r"(x.x), "=r"(x.y), "=r"(x.z), "=r"(x.w)
+                         : "l"(in + off + tt * 4096));
+            w[tt * 4 + 0] = x.x;
+            w[tt * 4 + 1] = x.y;
+            w[tt * 4 + 2] = x.z;
+            w[tt * 4 + 3] = x.w;
+        }
+#pragma unroll
+        for (int mm = 0; mm < LOGG; mm++) {
+            const int m = LOGG - 1 - mm;
+#pragma unroll
+            for (int b2 = 0; b2 < (G >> (m + 1)); b2++) {
+                const uint32_t cw = cross.w[(G >> (m + 1)) + b2], cwp = cross.wp[(G >> (m + 1)) + b2];
+#pragma unroll
+                for (int e = 0; e < (1 << m); e++) {
+                    const int t0 = (b2 << (m + 1)) + e;
+#pragma unroll
+                    for (int x = 0; x < 4; x++) {
+                        if (L4) {
+                            ct_bfly_l4(ct_l4_out_n(1, mm), w[t0 * 4 + x], w[(t0 + (1 << m)) * 4 + x], cw, cwp, q,
+                                       two_q, four_q, zero);
+                        } else if (mm == 0) {
+                            ct_bfly<false>(w[t0 * 4 + x], w[(t0 + (1 << m)) * 4 + x], cw, cwp, q, two_q, zero);
+                        } else {
+                            ct_bfly<true>(w[t0 * 4 + x], w[(t0 + (1 << m)) * 4 + x], cw, cwp, q, two_q, zero);
+                        }
+                    }
+                }
+            }
+        }
+        // the intermediate stays lazy: below 4q (classic) / kB1 * q (4q-lazy)
+#pragma unroll
+        for (int tt = 0; tt < G; tt++) {
+            *reinterpret_cast<uint4 *>(prm.out + off + tt * 4096) =
+                make_uint4(w[tt * 4], w[tt * 4 + 1], w[tt * 4 + 2], w[tt * 4 + 3]);
+        }
+        pending = p;
+        cq += num_teams;
+    }
+    publish();
+    if (j == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+    tmem_fence_before_sync();
+    __syncthreads();
+    if (warp == 0) tmem_dealloc_512(tmem_base);
+}
+
 // --------------------------------------------------------------------- host side
 int tile_maps(CUtensorMap *lo, CUtensorMap *hi, const int32_t *base, size_t tiles);  // kernels_fused.cu
 
@@ -367,6 +656,11 @@ static int tilecol_attrs() {
 }
 
 int tilecol_prepare() {
+    {
+        const auto attr = cudaFuncAttributeMaxDynamicSharedMemorySize;
+        NTTB200_CUDA(cudaFuncSetAttribute(tilecol_ct_kernel<false>, attr, kTC_SmemBytesCt));
+        NTTB200_CUDA(cudaFuncSetAttribute(tilecol_ct_kernel<true>, attr, kTC_SmemBytesCt));
+    }
     int rc = tilecol_attrs<1>();
     if (rc == NTTB200_OK) rc = tilecol_attrs<2>();
     if (rc == NTTB200_OK) rc = tilecol_attrs<3>();
@@ -485,6 +779,62 @@ int launch_tilecol_gs(nttb200_plan *p, const int32_t *d_in, const int32_t *d_b, 
     if (e != cudaSuccess) return cuda_fail(e, "tilecol_gs_kernel");
     if (e2 != cudaSuccess) return cuda_fail(e2, "cudaFreeAsync");
     p->last_path = dual ? "tilecol_persistent_dual" : "tilecol_persistent";
+    return NTTB200_OK;
+}
+
+// N = 2^16 forward transform in one persistent kernel: 4096 polynomials 0.811 ms against 0.901 ms
+// for column passes + tile pass (0.405 against 0.365 of the HBM roofline).
+// NTTB200_TILECOL_CT_OFF=1: the two-pass path (A/B).
+int launch_tilecol_ct(nttb200_plan *p, const int32_t *d_in, int32_t *d_out, size_t batch, cudaStream_t st) {
+    static const bool on = getenv("NTTB200_TILECOL_CT_OFF") == nullptr;
+    if (!on || p->logn != 16 || !p->d_tw_tile) return NTTB200_ERR_UNSUPPORTED;
+    const uint64_t tiles = (uint64_t) batch << 4;
+    if (tiles > 0x7fffffffull || ((uintptr_t) d_out & 15u) || ((uintptr_t) d_in & 15u)) return NTTB200_ERR_UNSUPPORTED;
+    static const long min_per_team = []() {
+        const char *e = getenv("NTTB200_TILECOL_MIN_TILES_PER_TEAM");
+        return e ? atol(e) : 12L;
+    }();
+    if (tiles < (uint64_t) p->sm_count * kM_Teams * (uint64_t) min_per_team) return NTTB200_ERR_UNSUPPORTED;
+    CUtensorMap m_lo, m_hi;
+    if (tile_maps(&m_lo, &m_hi, d_out, (size_t) tiles) != NTTB200_OK) return NTTB200_ERR_UNSUPPORTED;
+    TileColParams tp;
+    tp.out = reinterpret_cast<uint32_t *>(d_out);
+    tp.tw_tile = p->d_tw_tile;
+    tp.batch = (uint32_t) batch;
+    tp.q = p->q;
+    tp.zero = 0;
+    tp.qinv = tp.scale = tp.scale_shoup = 0;
+    tp.four_q = 4u * p->q;
+    uint64_t ctas = (tiles + kM_Teams - 1) / kM_Teams;
+    int grid = (int) (ctas < (uint64_t) p->sm_count ? ctas : (uint64_t) p->sm_count);
+    grid = grid < 2 ? 2 : (grid & ~1);
+    static const long lag_pct = []() {
+        const char *e = getenv("NTTB200_TILECOL_LAG_PCT");
+        return e ? atol(e) : 150L;
+    }();
+    const uint64_t lag_tiles = (uint64_t) grid * kM_Teams * (uint64_t) (lag_pct < 100 ? 100 : lag_pct) / 100;
+    tp.lag = (uint32_t) ((lag_tiles >> 4) + 2);
+    uint32_t *ctr = nullptr;
+    {
+        int rca = scratch_alloc_async((void **) &ctr, sizeof(uint32_t) * (batch + 1), st);
+        if (rca != NTTB200_OK) return rca;
+    }
+    NTTB200_CUDA(cudaMemsetAsync(ctr, 0, sizeof(uint32_t) * (batch + 1), st));
+    tp.done = ctr;
+    tp.error = ctr + batch;
+    if (use_l4(p)) {
+        tilecol_ct_kernel<true><<<grid, kM_Threads, kTC_SmemBytesCt, st>>>(
+            reinterpret_cast<const uint32_t *>(d_in), m_lo, m_hi, m_lo, m_hi, tp, p->cross_tw);
+    } else {
+        tilecol_ct_kernel<false><<<grid, kM_Threads, kTC_SmemBytesCt, st>>>(
+            reinterpret_cast<const uint32_t *>(d_in), m_lo, m_hi, m_lo, m_hi, tp, p->cross_tw);
+    }
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+    cudaError_t e = cudaGetLastError();
+    cudaError_t e2 = cudaFreeAsync(ctr, st);
+    if (e != cudaSuccess) return cuda_fail(e, "tilecol_ct_kernel");
+    if (e2 != cudaSuccess) return cuda_fail(e2, "cudaFreeAsync");
+    p->last_path = "tilecol_persistent_ct";
     return NTTB200_OK;
 }
 

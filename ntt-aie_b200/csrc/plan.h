@@ -118,6 +118,8 @@ int tilecol_prepare();
 int launch_tilecol_gs(nttb200_plan *p, const int32_t *d_in, const int32_t *d_b, int32_t *d_out,
                       size_t batch, cudaStream_t st);
 
+int launch_tilecol_ct(nttb200_plan *p, const int32_t *d_in, int32_t *d_out, size_t batch, cudaStream_t st);
+
 // one-kernel negacyclic product, N = 4096 (kernels_polymul.cu)
 int polymul_prepare();
 int launch_polymul4096(nttb200_plan *fwd, nttb200_plan *inv, const int32_t *d_a, const int32_t *d_b,

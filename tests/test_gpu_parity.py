@@ -997,6 +997,38 @@ def test_batch_minor_layout_adapter(lib, oracle_mod):
             assert np.array_equal(d_back.cpu().numpy(), oracle_mod.ntt_gs(a, table, Q29).T), (logn, batch)
 
 
+def test_persistent_forward_kernel_n65536(lib, oracle_mod):
+    """N = 2^16 forward transform in one persistent kernel (C-items first, T-items trailing; the
+    tile comes back from L2 by TMA behind a counter): a batch large enough to take it, a 4q-lazy
+    and a classic modulus, tables and one row pinned at q - 1; sampled rows against the oracle,
+    the whole batch against the two-pass path (small sub-batches), and in place."""
+    n = 1 << 16
+    rng = np.random.default_rng(31000)
+    for q, batch in ((Q29, 896), ((1 << 30) - 35, 890)):
+        table = rng.integers(0, q, n, dtype=np.int32)
+        table[1::2] = q - 1
+        a = rng.integers(0, q, (batch, n), dtype=np.int32)
+        a[0] = q - 1
+        rows = [0, 1, 447, batch - 1]
+        d_a = dev(a)
+        d_o = torch.empty_like(d_a)
+        d_c = torch.empty_like(d_a)
+        with lib.Plan(16, q, table) as plan:
+            plan.ct(d_a, d_o, batch)
+            torch.cuda.synchronize()
+            assert plan.last_path == "tilecol_persistent_ct", plan.last_path
+            assert np.array_equal(d_o.cpu().numpy()[rows], oracle_mod.ntt_ct(a[rows], table, q)), q
+            for s in range(0, batch, 128):
+                e = min(batch, s + 128)
+                plan.ct(d_a[s:e], d_c[s:e], e - s)
+            torch.cuda.synchronize()
+            assert plan.last_path != "tilecol_persistent_ct"
+            assert torch.equal(d_c, d_o), q
+            plan.ct(d_a, d_a, batch)
+            torch.cuda.synchronize()
+            assert torch.equal(d_a, d_o), (q, "in place")
+
+
 def test_cluster_kernel_n65536_opt_in(lib, oracle_mod):
     """The 2-CTA-cluster kernel for N = 2^16 (third round through distributed shared memory,
     NTTB200_CLUSTER16=1; measured slower than the persistent kernel, kept as the documented
