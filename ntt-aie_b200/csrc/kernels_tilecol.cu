@@ -603,6 +603,13 @@ tilecol_ct_kernel(const uint32_t *__restrict__ in, const __grid_constant__ CUten
             w[tt * 4 + 2] = x.z;
             w[tt * 4 + 3] = x.w;
         }
+        // the team's next C-item starts its way from HBM to L2 now (16 chunks of 1 KiB)
+        if (j < G && cq + num_teams < c_total) {
+            const uint32_t cn = cq + num_teams, pn = cn / G, kn = cn - pn * G;
+            asm volatile("cp.async.bulk.prefetch.L2.global [%0], 1024;" ::"l"(
+                             in + ((size_t) pn << (12 + LOGG)) + kn * (4096 / G) + (size_t) j * 4096)
+                         : "memory");
+        }
 #pragma unroll
         for (int mm = 0; mm < LOGG; mm++) {
             const int m = LOGG - 1 - mm;
