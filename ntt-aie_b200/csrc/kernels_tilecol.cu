@@ -165,14 +165,17 @@ tilecol_gs_kernel(const __grid_constant__ CUtensorMap map_lo, const __grid_const
         tma_load_3d(buf, &map_lo, bar, 0, 0, tile);
         tma_load_3d(buf + kF_PolyBytes / 2, &map_hi, bar, 0, 0, tile);
     }
-    // A warp publishes its share of a finished tile: its lanes' stores, then one release
-    // increment (2 warps per tile -> a polynomial is complete at 2G).  Deferred to the middle
+    // A team publishes a finished tile: its stores, then one release increment (a polynomial is
+    // complete at G).  Deferred to the middle
     // of the team's next T-item, when those stores have long left the SM and the fence is cheap.
     uint32_t pending = 0xffffffffu;
     auto publish = [&]() {
         if (pending != 0xffffffffu) {
-            __syncwarp();
-            if ((tid & 31) == 0) {
+            // ONE release per team: the team barrier orders the second warp's stores before the
+            // first warp's fence, whose cumulativity carries them along (half the MEMBAR.GPU
+            // round trips of a fence per warp; `pending` is team-uniform, so is this branch)
+            team_sync(team);
+            if ((tid & 63) == 0) {
                 asm volatile("fence.acq_rel.gpu;" ::: "memory");
                 asm volatile("red.relaxed.gpu.global.add.u32 [%0], 1;" ::"l"(prm.done + pending) : "memory");
             }
@@ -198,9 +201,9 @@ tilecol_gs_kernel(const __grid_constant__ CUtensorMap map_lo, const __grid_const
         while (cq < c_total && (!t_left || cq / G + prm.lag <= t_poly)) {
             const uint32_t p = cq / G, k = cq - p * G;
             if (!t_left) publish();
-            if (ctr_val < 2 * G) {
+            if (ctr_val < G) {
                 uint32_t spins = 0;
-                while ((ctr_val = ld_counter(prm.done + p)) < 2 * G) {
+                while ((ctr_val = ld_counter(prm.done + p)) < G) {
                     __nanosleep(64);
                     if (++spins > kTC_SpinLimit) {
                         atomicExch(prm.error, 1u);
@@ -334,7 +337,7 @@ tilecol_gs_kernel(const __grid_constant__ CUtensorMap map_lo, const __grid_const
             tma_load_3d(buf + kF_PolyBytes / 2, &map_hi, bar, 0, 0, tile);
         }
         publish();
-        if (ctr_val < 2 * G) prefetch_counter();   // the next C-item's polynomial was incomplete
+        if (ctr_val < G) prefetch_counter();   // the next C-item's polynomial was incomplete
         if (L4) {
             gs_round_l4<4>(v, tw2, q, two_q, four_q, zero);
         } else {
@@ -470,7 +473,7 @@ tilecol_ct_kernel(const uint32_t *__restrict__ in, const __grid_constant__ CUten
         if (j != 0 || loaded || i >= t_total) return;
         const uint32_t p = i / K;
         uint32_t spins = 0;
-        while (ld_counter(prm.done + p) < 2 * G) {
+        while (ld_counter(prm.done + p) < G) {
             if (!must) return;
             __nanosleep(64);
             if (++spins > kTC_SpinLimit) {
@@ -488,8 +491,11 @@ tilecol_ct_kernel(const uint32_t *__restrict__ in, const __grid_constant__ CUten
     uint32_t pending = 0xffffffffu;
     auto publish = [&]() {
         if (pending != 0xffffffffu) {
-            __syncwarp();
-            if ((tid & 31) == 0) {
+            // ONE release per team: the team barrier orders the second warp's stores before the
+            // first warp's fence, whose cumulativity carries them along (half the MEMBAR.GPU
+            // round trips of a fence per warp; `pending` is team-uniform, so is this branch)
+            team_sync(team);
+            if ((tid & 63) == 0) {
                 asm volatile("fence.acq_rel.gpu;" ::: "memory");
                 asm volatile("red.relaxed.gpu.global.add.u32 [%0], 1;" ::"l"(prm.done + pending) : "memory");
             }
