@@ -1,6 +1,6 @@
 """Launch each kernel family a few times (for `ncu -k regex:<name>` captures):
     python tools/dev/ncu_targets.py <which>
-which: headline | polymul | poly15 | tilecol16 | ct4096 | ct15 | fourstep_local"""
+which: headline | polymul | poly15 | tilecol16 | ct4096 | ct15 | ct16 | fourstep_local"""
 import os, sys, torch
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 import ntt_aie_b200 as nt
@@ -39,5 +39,7 @@ elif which == "ct4096":
     run(12, 28, "ct")
 elif which == "ct15":
     run(15, 26, "ct")
+elif which == "ct16":
+    run(16, 28, "ct")
 elif which == "fourstep_local":
     run(23, 23, "gs")
