@@ -740,7 +740,7 @@ int nttb200_rns_plan_create(nttb200_rns_plan **out, int device, uint32_t limbs, 
             const nttb200_plan *sp = rp->sub[l];
             uint4 pc = make_uint4(sp->q, 0, 0, 0);
             if (sp->q & 1u) {
-                pc.y = rns_inv_mod_2_32(sp->q);
+                pc.y = inv_mod_2_32(sp->q);
                 uint64_t sc = ((uint64_t) sp->n_inv << 32) % sp->q;
                 pc.z = (uint32_t) sc;
                 pc.w = (uint32_t) ((sc << 32) / sp->q);

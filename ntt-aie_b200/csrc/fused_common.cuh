@@ -443,4 +443,38 @@ __device__ __forceinline__ void ct_round_tmem_l4(uint32_t (&v)[64], uint32_t tad
     ct_blocks_l4<0, 0, 8, BL>(v, ta, q, two_q, four_q, zero);
 }
 
+// ---- pieces of the forward kernels that finish a row in two halves (tile_ct_h_kernel,
+// polyt_ct_kernel, tilecol_ct_kernel): classic or 4q-lazy blocks, and stages 4..0 of one half
+// with the private pairs streaming from tensor memory
+template <int S, int B0, int NB, int BIN, bool L4>
+__device__ __forceinline__ void ct_blocks_sel(uint32_t (&v)[64], const uint32_t *t, uint32_t q,
+                                              uint32_t two_q, uint32_t four_q, uint32_t zero) {
+    if (L4) {
+        ct_blocks_l4<S, B0, NB, BIN>(v, t, q, two_q, four_q, zero);
+    } else {
+        ct_blocks<S, B0, NB, true>(v, t, q, two_q, zero);
+    }
+}
+// stages 4..0 of half H (registers 32 H .. 32 H + 31); ts2 / ts345: the x16 groups at
+// columns 96 and 112 (stage 2, stages 3-5), already loaded
+template <int H, int B4, bool L4>
+__device__ __forceinline__ void ct_half_tmem(uint32_t (&v)[64], uint32_t taddr, const uint32_t *ts2,
+                                             const uint32_t *ts345, uint32_t q, uint32_t two_q,
+                                             uint32_t four_q, uint32_t zero) {
+    constexpr int B3 = ct_l4_out(B4), B2 = ct_l4_out(B3), B1 = ct_l4_out(B2), B0 = ct_l4_out(B1);
+    uint32_t ta[16], tb[16];
+    tmem_ld16(taddr + 64 + 16 * H, ta);                       // stage 1, blocks 8H .. 8H+7
+    ct_blocks_sel<4, H, 1, B4, L4>(v, ts345 + 8 + 2 * H, q, two_q, four_q, zero);
+    ct_blocks_sel<3, 2 * H, 2, B3, L4>(v, ts345 + 4 * H, q, two_q, four_q, zero);
+    ct_blocks_sel<2, 4 * H, 4, B2, L4>(v, ts2 + 8 * H, q, two_q, four_q, zero);
+    tmem_wait_ld16(ta);
+    tmem_ld16(taddr + 32 * H + 16, tb);                       // stage 0, blocks 16H+8 .. 16H+15
+    ct_blocks_sel<1, 8 * H, 8, B1, L4>(v, ta, q, two_q, four_q, zero);
+    tmem_wait_ld16(tb);
+    tmem_ld16(taddr + 32 * H, ta);                            // stage 0, blocks 16H .. 16H+7
+    ct_blocks_sel<0, 16 * H + 8, 8, B0, L4>(v, tb, q, two_q, four_q, zero);
+    tmem_wait_ld16(ta);
+    ct_blocks_sel<0, 16 * H, 8, B0, L4>(v, ta, q, two_q, four_q, zero);
+}
+
 }  // namespace nttb200

@@ -1323,12 +1323,6 @@ int launch_column_pass(nttb200_plan *p, const int32_t *in, int32_t *out, size_t 
     return column_pass_t<false>(p, in, out, batch, s0, k, st);
 }
 
-static uint32_t inv_mod_2_32(uint32_t q) {  // q odd
-    uint32_t x = q;                          // 3 correct bits; each Newton step doubles them
-    for (int i = 0; i < 5; i++) x *= 2u - q * x;
-    return x;
-}
-
 static TileParams tile_params(nttb200_plan *p, int32_t *d_out, size_t batch) {
     TileParams tp;
     tp.out = reinterpret_cast<uint32_t *>(d_out);
@@ -1776,6 +1770,5 @@ int rns_launch(int sm_count, int kind, const uint4 *d_tw_tile, const uint4 *h_po
     return NTTB200_OK;
 }
 
-uint32_t rns_inv_mod_2_32(uint32_t q) { return inv_mod_2_32(q); }
 
 }  // namespace nttb200

@@ -505,37 +505,6 @@ polyc_gs_kernel(const __grid_constant__ CUtensorMap map_lo, const __grid_constan
 // stages run.  (The first version staged the output in the tile buffer and could only load
 // the next polynomial after the store had drained -- the whole load latency was exposed:
 // 0.55 / 0.45 / 0.39 of the HBM roofline at N = 2^13 / 2^14 / 2^15 against 0.61 / 0.56 / 0.51.)
-template <int S, int B0, int NB, int BIN, bool L4>
-__device__ __forceinline__ void ct_blocks_sel(uint32_t (&v)[64], const uint32_t *t, uint32_t q,
-                                              uint32_t two_q, uint32_t four_q, uint32_t zero) {
-    if (L4) {
-        ct_blocks_l4<S, B0, NB, BIN>(v, t, q, two_q, four_q, zero);
-    } else {
-        ct_blocks<S, B0, NB, true>(v, t, q, two_q, zero);
-    }
-}
-// stages 4..0 of half H (registers 32 H .. 32 H + 31); ts2 / ts345: the x16 groups at
-// columns 96 and 112 (stage 2, stages 3-5), already loaded
-template <int H, int B4, bool L4>
-__device__ __forceinline__ void ct_half_tmem(uint32_t (&v)[64], uint32_t taddr, const uint32_t *ts2,
-                                             const uint32_t *ts345, uint32_t q, uint32_t two_q,
-                                             uint32_t four_q, uint32_t zero) {
-    constexpr int B3 = ct_l4_out(B4), B2 = ct_l4_out(B3), B1 = ct_l4_out(B2), B0 = ct_l4_out(B1);
-    uint32_t ta[16], tb[16];
-    tmem_ld16(taddr + 64 + 16 * H, ta);                       // stage 1, blocks 8H .. 8H+7
-    ct_blocks_sel<4, H, 1, B4, L4>(v, ts345 + 8 + 2 * H, q, two_q, four_q, zero);
-    ct_blocks_sel<3, 2 * H, 2, B3, L4>(v, ts345 + 4 * H, q, two_q, four_q, zero);
-    ct_blocks_sel<2, 4 * H, 4, B2, L4>(v, ts2 + 8 * H, q, two_q, four_q, zero);
-    tmem_wait_ld16(ta);
-    tmem_ld16(taddr + 32 * H + 16, tb);                       // stage 0, blocks 16H+8 .. 16H+15
-    ct_blocks_sel<1, 8 * H, 8, B1, L4>(v, ta, q, two_q, four_q, zero);
-    tmem_wait_ld16(tb);
-    tmem_ld16(taddr + 32 * H, ta);                            // stage 0, blocks 16H .. 16H+7
-    ct_blocks_sel<0, 16 * H + 8, 8, B0, L4>(v, tb, q, two_q, four_q, zero);
-    tmem_wait_ld16(ta);
-    ct_blocks_sel<0, 16 * H, 8, B0, L4>(v, ta, q, two_q, four_q, zero);
-}
-
 template <int LOGG, bool L4>
 __global__ void __launch_bounds__(kM_Threads, 1)
 polyt_ct_kernel(const __grid_constant__ CUtensorMap map_lo, const __grid_constant__ CUtensorMap map_hi,
@@ -750,12 +719,6 @@ int polyt_prepare() {
     return rc;
 }
 
-static uint32_t py_inv_mod_2_32(uint32_t q) {  // q odd
-    uint32_t x = q;
-    for (int i = 0; i < 5; i++) x *= 2u - q * x;
-    return x;
-}
-
 static bool polyt_enabled() {
     static const bool on = getenv("NTTB200_POLY_NO_TMEM") == nullptr;
     return on;
@@ -805,7 +768,7 @@ int launch_polyt_gs(nttb200_plan *p, const int32_t *d_in, const int32_t *d_b, in
     tp.four_q = 4u * p->q;
     if (d_b) {
         if (tile_maps(&b_lo, &b_hi, d_b, (size_t) tiles) != NTTB200_OK) return NTTB200_ERR_UNSUPPORTED;
-        tp.qinv = py_inv_mod_2_32(p->q);
+        tp.qinv = inv_mod_2_32(p->q);
         const uint64_t sc = ((uint64_t) p->n_inv << 32) % p->q;
         tp.scale = (uint32_t) sc;
         tp.scale_shoup = (uint32_t) ((sc << 32) / p->q);
@@ -852,7 +815,7 @@ int launch_polyc_gs(nttb200_plan *p, const int32_t *d_in, const int32_t *d_b, in
     tp.four_q = 4u * p->q;
     if (d_b) {
         if (tile_maps(&b_lo, &b_hi, d_b, (size_t) tiles) != NTTB200_OK) return NTTB200_ERR_UNSUPPORTED;
-        tp.qinv = py_inv_mod_2_32(p->q);
+        tp.qinv = inv_mod_2_32(p->q);
         const uint64_t sc = ((uint64_t) p->n_inv << 32) % p->q;
         tp.scale = (uint32_t) sc;
         tp.scale_shoup = (uint32_t) ((sc << 32) / p->q);

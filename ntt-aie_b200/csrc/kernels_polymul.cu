@@ -326,12 +326,6 @@ int polymul_prepare() {
     return NTTB200_OK;
 }
 
-static uint32_t pm_inv_mod_2_32(uint32_t q) {  // q odd
-    uint32_t x = q;
-    for (int i = 0; i < 5; i++) x *= 2u - q * x;
-    return x;
-}
-
 // c = a (*) b for `batch` products of N = 4096 in one launch.  fwd / inv: plans of the
 // psi^bitrev / psi^-bitrev tables with their N = 4096 layouts built (fused_prepare).
 int launch_polymul4096(nttb200_plan *fwd, nttb200_plan *inv, const int32_t *d_a, const int32_t *d_b,
@@ -364,7 +358,7 @@ int launch_polymul4096_strided(nttb200_plan *fwd, nttb200_plan *inv, const int32
     prm.batch = (uint32_t) batch;
     prm.q = fwd->q;
     prm.zero = 0;
-    prm.qinv = pm_inv_mod_2_32(fwd->q);
+    prm.qinv = inv_mod_2_32(fwd->q);
     const uint64_t sc = ((uint64_t) inv->n_inv << 32) % inv->q;
     prm.scale = (uint32_t) sc;
     prm.scale_shoup = (uint32_t) ((sc << 32) / inv->q);

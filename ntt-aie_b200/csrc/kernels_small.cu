@@ -519,12 +519,6 @@ int small_prepare(nttb200_plan *p) {
     }
 }
 
-static uint32_t small_inv_mod_2_32(uint32_t q) {
-    uint32_t x = q;
-    for (int i = 0; i < 5; i++) x *= 2u - q * x;
-    return x;
-}
-
 // kind: 0 = GS, 1 = GS with ans_order store, 2 = GS of d_in (*) d_b scaled by N^-1, 3 = CT
 template <int LOGN>
 static void small_launch_t(int kind, int grid, cudaStream_t st, const CUtensorMap &lo,
@@ -604,7 +598,7 @@ int launch_small(nttb200_plan *p, int kind, const int32_t *d_in, const int32_t *
     prm.zero = 0;
     prm.qinv = prm.scale = prm.scale_shoup = 0;
     if (kind == 2) {
-        prm.qinv = small_inv_mod_2_32(p->q);
+        prm.qinv = inv_mod_2_32(p->q);
         uint64_t sc = ((uint64_t) p->n_inv << 32) % p->q;
         prm.scale = (uint32_t) sc;
         prm.scale_shoup = (uint32_t) ((sc << 32) / p->q);

@@ -368,35 +368,6 @@ tilecol_gs_kernel(const __grid_constant__ CUtensorMap map_lo, const __grid_const
 constexpr int kTC_StageBase = kM_Teams * kF_PolyBytes + 128 + 8 * 512;
 constexpr int kTC_SmemBytesCt = ((kTC_StageBase + 1023) / 1024) * 1024 + kM_Teams * (kF_PolyBytes / 2) + 1024;
 
-template <int S, int B0, int NB, int BIN, bool L4>
-__device__ __forceinline__ void tc_ct_blocks(uint32_t (&v)[64], const uint32_t *t, uint32_t q,
-                                             uint32_t two_q, uint32_t four_q, uint32_t zero) {
-    if (L4) {
-        ct_blocks_l4<S, B0, NB, BIN>(v, t, q, two_q, four_q, zero);
-    } else {
-        ct_blocks<S, B0, NB, true>(v, t, q, two_q, zero);
-    }
-}
-template <int H, int B4, bool L4>
-__device__ __forceinline__ void tc_ct_half(uint32_t (&v)[64], uint32_t taddr, const uint32_t *ts2,
-                                           const uint32_t *ts345, uint32_t q, uint32_t two_q,
-                                           uint32_t four_q, uint32_t zero) {
-    constexpr int B3 = ct_l4_out(B4), B2 = ct_l4_out(B3), B1 = ct_l4_out(B2), B0 = ct_l4_out(B1);
-    uint32_t ta[16], tb[16];
-    tmem_ld16(taddr + 64 + 16 * H, ta);
-    tc_ct_blocks<4, H, 1, B4, L4>(v, ts345 + 8 + 2 * H, q, two_q, four_q, zero);
-    tc_ct_blocks<3, 2 * H, 2, B3, L4>(v, ts345 + 4 * H, q, two_q, four_q, zero);
-    tc_ct_blocks<2, 4 * H, 4, B2, L4>(v, ts2 + 8 * H, q, two_q, four_q, zero);
-    tmem_wait_ld16(ta);
-    tmem_ld16(taddr + 32 * H + 16, tb);
-    tc_ct_blocks<1, 8 * H, 8, B1, L4>(v, ta, q, two_q, four_q, zero);
-    tmem_wait_ld16(tb);
-    tmem_ld16(taddr + 32 * H, ta);
-    tc_ct_blocks<0, 16 * H + 8, 8, B0, L4>(v, tb, q, two_q, four_q, zero);
-    tmem_wait_ld16(ta);
-    tc_ct_blocks<0, 16 * H, 8, B0, L4>(v, ta, q, two_q, four_q, zero);
-}
-
 template <bool L4>
 __global__ void __launch_bounds__(kM_Threads, 1)
 tilecol_ct_kernel(const uint32_t *__restrict__ in, const __grid_constant__ CUtensorMap mid_lo,
@@ -557,14 +528,14 @@ tilecol_ct_kernel(const uint32_t *__restrict__ in, const __grid_constant__ CUten
             tmem_ld16(tw1 + 112, ts345);
             tmem_wait_ld16(ts345);
             tmem_ld16(tw1 + 96, ts2);
-            tc_ct_blocks<5, 0, 1, kB2, L4>(v, ts345 + 12, q, two_q, four_q, zero);
+            ct_blocks_sel<5, 0, 1, kB2, L4>(v, ts345 + 12, q, two_q, four_q, zero);
             tmem_wait_ld16(ts2);
 #pragma unroll
             for (int h = 0; h < 2; h++) {
                 if (h == 0) {
-                    tc_ct_half<0, kB4, L4>(v, tw1, ts2, ts345, q, two_q, four_q, zero);
+                    ct_half_tmem<0, kB4, L4>(v, tw1, ts2, ts345, q, two_q, four_q, zero);
                 } else {
-                    tc_ct_half<1, kB4, L4>(v, tw1, ts2, ts345, q, two_q, four_q, zero);
+                    ct_half_tmem<1, kB4, L4>(v, tw1, ts2, ts345, q, two_q, four_q, zero);
                     if (j == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
                     team_sync(team);
                 }
@@ -681,12 +652,6 @@ int tilecol_prepare() {
     return rc;
 }
 
-static uint32_t tc_inv_mod_2_32(uint32_t q) {  // q odd
-    uint32_t x = q;
-    for (int i = 0; i < 5; i++) x *= 2u - q * x;
-    return x;
-}
-
 // which transform lengths take this kernel: 16 by default -- measured at 2^28 coefficients:
 // 0.439 of the HBM roofline against 0.403 for the two passes; for N = 2^13..2^15 the
 // one-CTA-per-polynomial kernels of kernels_poly.cu are faster (0.50/0.49/0.42 against
@@ -746,7 +711,7 @@ int launch_tilecol_gs(nttb200_plan *p, const int32_t *d_in, const int32_t *d_b, 
     tp.four_q = 4u * p->q;
     if (d_b) {
         if (tile_maps(&b_lo, &b_hi, d_b, (size_t) tiles) != NTTB200_OK) return NTTB200_ERR_UNSUPPORTED;
-        tp.qinv = tc_inv_mod_2_32(p->q);
+        tp.qinv = inv_mod_2_32(p->q);
         const uint64_t sc = ((uint64_t) p->n_inv << 32) % p->q;
         tp.scale = (uint32_t) sc;
         tp.scale_shoup = (uint32_t) ((sc << 32) / p->q);

@@ -168,7 +168,12 @@ int launch_gs_range_scatter(nttb200_plan *p, int32_t *d_buf, int sb, int se, voi
 int rns_launch(int sm_count, int kind, const uint4 *d_tw_tile, const uint4 *h_pos, uint32_t limbs,
                const int32_t *d_a, const int32_t *d_b, int32_t *d_out, size_t batch,
                cudaStream_t st);
-uint32_t rns_inv_mod_2_32(uint32_t q);
+// q^-1 mod 2^32 for odd q (Montgomery products): Newton iteration, 3 correct bits doubling per step
+inline uint32_t inv_mod_2_32(uint32_t q) {
+    uint32_t x = q;
+    for (int i = 0; i < 5; i++) x *= 2u - q * x;
+    return x;
+}
 constexpr int kRnsTwTile = 32 * 65;  // uint4s per channel in d_tw_tile (kernels_multi.cu)
 int launch_multi_ct(nttb200_plan *p, const int32_t *d_in, int32_t *d_out, size_t batch,
                     cudaStream_t st);
