@@ -842,6 +842,6 @@ const char *nttb200_plan_last_path(const nttb200_plan *p) {
 }
 uint32_t nttb200_plan_logn(const nttb200_plan *p) { return p ? p->logn : 0; }
 uint32_t nttb200_plan_modulus(const nttb200_plan *p) { return p ? p->q : 0; }
-const char *nttb200_version(void) { return "nttb200 0.2 (sm_100a)"; }
+const char *nttb200_version(void) { return "nttb200 0.3 (sm_100a)"; }
 
 }  // extern "C"
