@@ -65,6 +65,11 @@ int cuda_fail(cudaError_t e, const char *what) {
                : NTTB200_ERR_CUDA;
 }
 
+int fail_msg(int status, const char *msg) {
+    snprintf(t_err, sizeof(t_err), "%s", msg);
+    return status;
+}
+
 static uint64_t powmod64(uint64_t b, uint64_t e, uint64_t m) {
     uint64_t r = 1 % m;
     b %= m;
@@ -211,6 +216,7 @@ static int plan_begin(nttb200_plan **out, int device, uint32_t logn, uint32_t q,
 static void plan_abort(nttb200_plan *p) {
     fused_release(p);
     multi_release(p);
+    tilecol_release(p);
     if (p->d_tw) cudaFree(p->d_tw);
     delete p;
 }
@@ -320,6 +326,7 @@ int nttb200_plan_destroy(nttb200_plan *p) {
     host_release(p);
     fused_release(p);
     multi_release(p);
+    tilecol_release(p);
     if (p->d_tw) cudaFree(p->d_tw);
     delete p;
     if (g_live_plans.fetch_sub(1) == 1) scratch_trim_all();   // last plan: give the scratch pages back

@@ -206,7 +206,10 @@ tilecol_gs_kernel(const __grid_constant__ CUtensorMap map_lo, const __grid_const
                 while ((ctr_val = ld_counter(prm.done + p)) < G) {
                     __nanosleep(64);
                     if (++spins > kTC_SpinLimit) {
-                        atomicExch(prm.error, 1u);
+                        {
+                            *reinterpret_cast<volatile uint32_t *>(prm.error) = 1u;   // mapped host word
+                            __threadfence_system();
+                        }
                         break;
                     }
                 }
@@ -448,7 +451,10 @@ tilecol_ct_kernel(const uint32_t *__restrict__ in, const __grid_constant__ CUten
             if (!must) return;
             __nanosleep(64);
             if (++spins > kTC_SpinLimit) {
-                atomicExch(prm.error, 1u);
+                {
+                            *reinterpret_cast<volatile uint32_t *>(prm.error) = 1u;   // mapped host word
+                            __threadfence_system();
+                        }
                 break;
             }
         }
@@ -672,6 +678,28 @@ static bool tilecol_enabled(uint32_t logn) {
     return (mask >> logn) & 1u;
 }
 
+// The error word of the plan: mapped host memory, so the host can read it without a
+// synchronisation.  Checked (and cleared) at the start of the next persistent launch.
+static int tilecol_error_word(nttb200_plan *p) {
+    if (!p->tc_err_host) {
+        NTTB200_CUDA(cudaHostAlloc((void **) &p->tc_err_host, sizeof(uint32_t), cudaHostAllocMapped));
+        *p->tc_err_host = 0;
+        NTTB200_CUDA(cudaHostGetDevicePointer((void **) &p->tc_err_dev, p->tc_err_host, 0));
+    }
+    if (*reinterpret_cast<volatile uint32_t *>(p->tc_err_host)) {
+        *p->tc_err_host = 0;
+        return fail_msg(NTTB200_ERR_CUDA,
+                        "an earlier persistent tile/column launch on this plan gave up waiting for a "
+                        "polynomial counter: its output is incomplete");
+    }
+    return NTTB200_OK;
+}
+
+void tilecol_release(nttb200_plan *p) {
+    if (p->tc_err_host) cudaFreeHost(p->tc_err_host);
+    p->tc_err_host = p->tc_err_dev = nullptr;
+}
+
 template <int LOGG, bool DUAL>
 static void tilecol_gs_launch(int grid, cudaStream_t st, const CUtensorMap &a_lo, const CUtensorMap &a_hi,
                               const CUtensorMap &b_lo, const CUtensorMap &b_hi, const TileColParams &tp,
@@ -732,6 +760,10 @@ int launch_tilecol_gs(nttb200_plan *p, const int32_t *d_in, const int32_t *d_b, 
     const uint64_t lag_tiles = (uint64_t) grid * kM_Teams * (uint64_t) (lag_pct < 100 ? 100 : lag_pct) / 100;
     tp.lag = (uint32_t) ((lag_tiles >> logg) + 2);   // > one queue step (grid * 8 / G polynomials)
     // counters: one per polynomial + the error word, stream-ordered scratch
+    {
+        int rce = tilecol_error_word(p);
+        if (rce != NTTB200_OK) return rce;
+    }
     uint32_t *ctr = nullptr;
     {
         int rca = scratch_alloc_async((void **) &ctr, sizeof(uint32_t) * (batch + 1), st);
@@ -739,7 +771,7 @@ int launch_tilecol_gs(nttb200_plan *p, const int32_t *d_in, const int32_t *d_b, 
     }
     NTTB200_CUDA(cudaMemsetAsync(ctr, 0, sizeof(uint32_t) * (batch + 1), st));
     tp.done = ctr;
-    tp.error = ctr + batch;
+    tp.error = p->tc_err_dev;
     const bool dual = d_b != nullptr, l4 = use_l4(p);
     switch (logg * 2 + (dual ? 1 : 0)) {
         case 2: tilecol_gs_launch<1, false>(grid, st, a_lo, a_hi, b_lo, b_hi, tp, p->cross_tw, l4); break;
@@ -792,6 +824,10 @@ int launch_tilecol_ct(nttb200_plan *p, const int32_t *d_in, int32_t *d_out, size
     }();
     const uint64_t lag_tiles = (uint64_t) grid * kM_Teams * (uint64_t) (lag_pct < 100 ? 100 : lag_pct) / 100;
     tp.lag = (uint32_t) ((lag_tiles >> 4) + 2);
+    {
+        int rce = tilecol_error_word(p);
+        if (rce != NTTB200_OK) return rce;
+    }
     uint32_t *ctr = nullptr;
     {
         int rca = scratch_alloc_async((void **) &ctr, sizeof(uint32_t) * (batch + 1), st);
@@ -799,7 +835,7 @@ int launch_tilecol_ct(nttb200_plan *p, const int32_t *d_in, int32_t *d_out, size
     }
     NTTB200_CUDA(cudaMemsetAsync(ctr, 0, sizeof(uint32_t) * (batch + 1), st));
     tp.done = ctr;
-    tp.error = ctr + batch;
+    tp.error = p->tc_err_dev;
     if (use_l4(p)) {
         tilecol_ct_kernel<true><<<grid, kM_Threads, kTC_SmemBytesCt, st>>>(
             reinterpret_cast<const uint32_t *>(d_in), m_lo, m_hi, m_lo, m_hi, tp, p->cross_tw);

@@ -46,6 +46,10 @@ struct nttb200_plan {
     uint4 *d_tw_tile = nullptr;      // [N/4096][32][65] tile-pass twiddles (logn 12..26)
     nttb200::UniformTw uni_gs{};     // round-2 uniform twiddles, GS network
     nttb200::CrossTw cross_tw{};     // table[1..15] (logn >= 13)
+    // persistent kernels (kernels_tilecol.cu): a waiter that gives up sets this word (pinned,
+    // mapped host memory, allocated on first use); the next launch on the plan reports it
+    uint32_t *tc_err_host = nullptr;
+    uint32_t *tc_err_dev = nullptr;
     int sm_count = 148;
     // written by every launch, possibly from several host threads driving different streams
     std::atomic<const char *> last_path{"none"};
@@ -119,6 +123,8 @@ int launch_tilecol_gs(nttb200_plan *p, const int32_t *d_in, const int32_t *d_b, 
                       size_t batch, cudaStream_t st);
 
 int launch_tilecol_ct(nttb200_plan *p, const int32_t *d_in, int32_t *d_out, size_t batch, cudaStream_t st);
+void tilecol_release(nttb200_plan *p);
+int fail_msg(int status, const char *msg);   // sets nttb200_last_error, returns status
 
 // one-kernel negacyclic product, N = 4096 (kernels_polymul.cu)
 int polymul_prepare();
