@@ -681,7 +681,7 @@ static bool tilecol_enabled(uint32_t logn) {
 // The error word of the plan: mapped host memory, so the host can read it without a
 // synchronisation.  Checked (and cleared) at the start of the next persistent launch.
 static int tilecol_error_word(nttb200_plan *p) {
-    std::lock_guard<std::mutex> lock(p->host_mu);   // plans may be driven from several host threads
+    std::lock_guard<std::mutex> lock(p->tc_mu);   // plans may be driven from several host threads
     if (!p->tc_err_host) {
         NTTB200_CUDA(cudaHostAlloc((void **) &p->tc_err_host, sizeof(uint32_t), cudaHostAllocMapped));
         *p->tc_err_host = 0;

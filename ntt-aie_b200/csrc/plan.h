@@ -50,6 +50,7 @@ struct nttb200_plan {
     // mapped host memory, allocated on first use); the next launch on the plan reports it
     uint32_t *tc_err_host = nullptr;
     uint32_t *tc_err_dev = nullptr;
+    std::mutex tc_mu;                // guards the lazy allocation above (not host_mu: gs_host holds that one)
     int sm_count = 148;
     // written by every launch, possibly from several host threads driving different streams
     std::atomic<const char *> last_path{"none"};
