@@ -54,7 +54,8 @@ struct RnsConsts {
 // 2 = shared-memory table per SEGMENT: the CTA's range of position-major tiles is cut
 //     at position changes, the table of the segment's position is staged between two
 //     __syncthreads (batched large-N and RNS workloads, where a segment is long).
-template <bool DUAL, bool RNS, int TWMODE = 0>
+// L4: 4q-lazy butterflies (q < 2^29, single modulus); the tile's output is canonical either way.
+template <bool DUAL, bool RNS, int TWMODE = 0, bool L4 = false>
 __global__ void __launch_bounds__(kM_Threads, 1)
 tile_gs_kernel(const __grid_constant__ CUtensorMap map_lo, const __grid_constant__ CUtensorMap map_hi,
                const __grid_constant__ CUtensorMap map_b_lo,
@@ -71,7 +72,8 @@ tile_gs_kernel(const __grid_constant__ CUtensorMap map_lo, const __grid_constant
     const int j = tid & 63;
     uint32_t q = prm.q, two_q = 2u * prm.q;
     uint32_t qinv = prm.qinv, scale = prm.scale, scale_shoup = prm.scale_shoup;
-    const uint32_t zero = prm.zero;
+    const uint32_t zero = prm.zero, four_q = prm.four_q;
+    static_assert(!L4 || !RNS, "the channels of an RNS batch sit just below 2^30");
 
     const uint32_t tws = bar_base + 64;
     if (TWMODE == 1) {
@@ -177,7 +179,11 @@ tile_gs_kernel(const __grid_constant__ CUtensorMap map_lo, const __grid_constant
                 }
             }
         }
-        if (TWMODE != 0) {
+        if (L4 && TWMODE != 0) {
+            gs_round_l4<(DUAL ? 2 : 1)>(v, TwShared{tws + j * 16}, q, two_q, four_q, zero);
+        } else if (L4) {
+            gs_round_l4<(DUAL ? 2 : 1)>(v, TwGlobal{tw + j}, q, two_q, four_q, zero);
+        } else if (TWMODE != 0) {
             gs_round<DUAL>(v, TwShared{tws + j * 16}, q, two_q, zero);
         } else {
             gs_round<DUAL>(v, TwGlobal{tw + j}, q, two_q, zero);
@@ -205,7 +211,11 @@ tile_gs_kernel(const __grid_constant__ CUtensorMap map_lo, const __grid_constant
                 tma_load_3d(buf + kF_PolyBytes / 2, &map_hi, bar, 0, 0, (int) tile_cur);
             }
         }
-        if (TWMODE != 0) {
+        if (L4 && TWMODE != 0) {
+            gs_round_l4<4>(v, TwShared{tws + 64 * 16}, q, two_q, four_q, zero);
+        } else if (L4) {
+            gs_round_l4<4>(v, TwGlobal{tw + 64}, q, two_q, four_q, zero);
+        } else if (TWMODE != 0) {
             gs_round<true>(v, TwShared{tws + 64 * 16}, q, two_q, zero);
         } else {
             gs_round<true>(v, TwGlobal{tw + 64}, q, two_q, zero);
@@ -214,7 +224,12 @@ tile_gs_kernel(const __grid_constant__ CUtensorMap map_lo, const __grid_constant
         uint32_t *dst = prm.out + (size_t) tile_store * 4096 + j;
 #pragma unroll
         for (int i = 0; i < 64; i++) {
-            uint32_t r = DUAL ? shoup_mul_lazy(v[i], scale, scale_shoup, q) : v[i];
+            uint32_t r = v[i];
+            if (DUAL) {
+                r = shoup_mul_lazy(r, scale, scale_shoup, q);   // any word in, [0, 2q) out
+            } else if (L4 && !(i & 32)) {
+                r = min(r - two_q, r);                          // a sum of the last stage: below 4q
+            }
             dst[i * 64] = min(r - q, r);
         }
     }
@@ -1221,6 +1236,10 @@ int multi_set_attrs() {
     NTTB200_CUDA(cudaFuncSetAttribute(tile_gs_kernel<false, true, 2>, attr, kM_SmemBytesTw));
     NTTB200_CUDA(cudaFuncSetAttribute(tile_gs_kernel<true, true, 2>, attr, kM_SmemBytesTw));
     NTTB200_CUDA(cudaFuncSetAttribute(tile_gs_kernel<true, false, 1>, attr, kM_SmemBytesTw));
+    NTTB200_CUDA(cudaFuncSetAttribute(tile_gs_kernel<false, false, 0, true>, attr, kM_SmemBytes));
+    NTTB200_CUDA(cudaFuncSetAttribute(tile_gs_kernel<true, false, 0, true>, attr, kM_SmemBytes));
+    NTTB200_CUDA(cudaFuncSetAttribute(tile_gs_kernel<false, false, 2, true>, attr, kM_SmemBytesTw));
+    NTTB200_CUDA(cudaFuncSetAttribute(tile_gs_kernel<true, false, 2, true>, attr, kM_SmemBytesTw));
     NTTB200_CUDA(cudaFuncSetAttribute(tile_ct_kernel<false, true>, attr, kM_SmemBytesTw));
     NTTB200_CUDA(cudaFuncSetAttribute(tile_ct_h_kernel<false>, attr, kH_SmemBytes));
     NTTB200_CUDA(cudaFuncSetAttribute(tile_ct_h_kernel<true>, attr, kH_SmemBytes));
@@ -1409,6 +1428,7 @@ static int launch_multi_gs_once(nttb200_plan *p, const int32_t *d_in, const int3
     }
     TileParams tp = tile_params(p, d_out, batch);
     int grid = tile_grid(p, tiles);
+    const bool l4 = use_l4(p) && tp.chunks > 1;
     if (d_b) {
         if (tile_maps(&b_lo, &b_hi, d_b, (size_t) tiles) != NTTB200_OK) return NTTB200_ERR_UNSUPPORTED;
         tp.qinv = inv_mod_2_32(p->q);
@@ -1419,9 +1439,15 @@ static int launch_multi_gs_once(nttb200_plan *p, const int32_t *d_in, const int3
         if (tp.chunks == 1) {  // N = 4096: one table for every tile, kept in shared memory
             tile_gs_kernel<true, false, 1><<<grid, kM_Threads, kM_SmemBytesTw, st>>>(
                 map_lo, map_hi, b_lo, b_hi, tp, kNoRns);
+        } else if (seg_tables(batch) && l4) {
+            tile_gs_kernel<true, false, 2, true><<<grid, kM_Threads, kM_SmemBytesTw, st>>>(
+                map_lo, map_hi, b_lo, b_hi, tp, kNoRns);
         } else if (seg_tables(batch)) {
             tile_gs_kernel<true, false, 2><<<grid, kM_Threads, kM_SmemBytesTw, st>>>(
                 map_lo, map_hi, b_lo, b_hi, tp, kNoRns);
+        } else if (l4) {
+            tile_gs_kernel<true, false, 0, true><<<grid, kM_Threads, kM_SmemBytes, st>>>(map_lo, map_hi, b_lo,
+                                                                                         b_hi, tp, kNoRns);
         } else {
             tile_gs_kernel<true, false><<<grid, kM_Threads, kM_SmemBytes, st>>>(map_lo, map_hi, b_lo,
                                                                                 b_hi, tp, kNoRns);
@@ -1429,9 +1455,15 @@ static int launch_multi_gs_once(nttb200_plan *p, const int32_t *d_in, const int3
     } else if (tp.chunks == 1) {
         tile_gs_kernel<false, false, 1><<<grid, kM_Threads, kM_SmemBytesTw, st>>>(
             map_lo, map_hi, map_lo, map_hi, tp, kNoRns);
+    } else if (seg_tables(batch) && l4) {
+        tile_gs_kernel<false, false, 2, true><<<grid, kM_Threads, kM_SmemBytesTw, st>>>(
+            map_lo, map_hi, map_lo, map_hi, tp, kNoRns);
     } else if (seg_tables(batch)) {
         tile_gs_kernel<false, false, 2><<<grid, kM_Threads, kM_SmemBytesTw, st>>>(
             map_lo, map_hi, map_lo, map_hi, tp, kNoRns);
+    } else if (l4) {
+        tile_gs_kernel<false, false, 0, true><<<grid, kM_Threads, kM_SmemBytes, st>>>(map_lo, map_hi, map_lo,
+                                                                                      map_hi, tp, kNoRns);
     } else {
         tile_gs_kernel<false, false><<<grid, kM_Threads, kM_SmemBytes, st>>>(map_lo, map_hi, map_lo,
                                                                              map_hi, tp, kNoRns);
