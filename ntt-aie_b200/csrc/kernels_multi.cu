@@ -412,7 +412,7 @@ poly_gs_kernel(const __grid_constant__ CUtensorMap map_lo, const __grid_constant
 // STAGED (not with SMEM_TW / MULT): an 8 KiB staging slot per team takes the output in two
 // halves (see tile_ct_h_kernel below), so the tile buffer receives the prefetch of the team's next
 // tile as soon as the rows are in registers instead of after the store has drained.
-template <bool RNS, bool SMEM_TW = false, bool MULT = false, bool STAGED = false>
+template <bool RNS, bool SMEM_TW = false, bool MULT = false, bool STAGED = false, bool L4 = false>
 __global__ void __launch_bounds__(kM_Threads, 1)
 tile_ct_kernel(const __grid_constant__ CUtensorMap map_lo, const __grid_constant__ CUtensorMap map_hi,
                const __grid_constant__ CUtensorMap out_lo, const __grid_constant__ CUtensorMap out_hi,
@@ -432,6 +432,10 @@ tile_ct_kernel(const __grid_constant__ CUtensorMap map_lo, const __grid_constant
 
     const uint32_t tws = bar_base + 64;
     static_assert(!STAGED || (!SMEM_TW && !MULT), "the staged variant has no table / product form");
+    static_assert(!L4 || (STAGED && !RNS), "4q-lazy only in the staged single-modulus form");
+    const uint32_t four_q = prm.four_q;
+    constexpr int kBCol = ct_l4_out_n(1, 6), kB4 = ct_l4_out(kBCol), kB3 = ct_l4_out(kB4), kB2 = ct_l4_out(kB3),
+                  kB1 = ct_l4_out(kB2), kB0 = ct_l4_out(kB1), kBRow = ct_l4_out(kB0);
     const uint32_t stg = ((bar_base + 64 + 1023u) & ~1023u) + team * (kF_PolyBytes / 2);
     const uint32_t st_row = stg + j * 128;
     if (SMEM_TW) {
@@ -486,7 +490,9 @@ tile_ct_kernel(const __grid_constant__ CUtensorMap map_lo, const __grid_constant
         for (int i = 0; i < 64; i++) {
             v[i] = lds32(r2_col + i * 128 + (r2_chunk ^ ((i & 7) << 4)));
         }
-        if (SMEM_TW) {
+        if (L4) {
+            ct_round_l4<1>(v, TwGlobal{tw + 64}, q, two_q, four_q, zero);
+        } else if (SMEM_TW) {
             ct_round<false>(v, TwShared{tws + 64 * 16}, q, two_q, zero);
         } else {
             ct_round<false>(v, TwGlobal{tw + 64}, q, two_q, zero);
@@ -533,21 +539,25 @@ tile_ct_kernel(const __grid_constant__ CUtensorMap map_lo, const __grid_constant
             }
             // ---- rows: stage 5 pairs the halves, stages 4..0 run per half
             const TwGlobal twr{tw + j};
-            ct_stage_t<5, true>(v, twr, q, two_q, zero);
+            if (L4) {
+                ct_stage_l4<5, kBCol>(v, twr, q, two_q, four_q, zero);
+            } else {
+                ct_stage_t<5, true>(v, twr, q, two_q, zero);
+            }
 #pragma unroll
             for (int h = 0; h < 2; h++) {
                 if (h == 0) {
-                    ct_half_stage<4, 0, -1>(v, twr, q, two_q, 0u, zero);
-                    ct_half_stage<3, 0, -1>(v, twr, q, two_q, 0u, zero);
-                    ct_half_stage<2, 0, -1>(v, twr, q, two_q, 0u, zero);
-                    ct_half_stage<1, 0, -1>(v, twr, q, two_q, 0u, zero);
-                    ct_half_stage<0, 0, -1>(v, twr, q, two_q, 0u, zero);
+                    ct_half_stage<4, 0, (L4 ? kB4 : -1)>(v, twr, q, two_q, four_q, zero);
+                    ct_half_stage<3, 0, (L4 ? kB3 : -1)>(v, twr, q, two_q, four_q, zero);
+                    ct_half_stage<2, 0, (L4 ? kB2 : -1)>(v, twr, q, two_q, four_q, zero);
+                    ct_half_stage<1, 0, (L4 ? kB1 : -1)>(v, twr, q, two_q, four_q, zero);
+                    ct_half_stage<0, 0, (L4 ? kB0 : -1)>(v, twr, q, two_q, four_q, zero);
                 } else {
-                    ct_half_stage<4, 1, -1>(v, twr, q, two_q, 0u, zero);
-                    ct_half_stage<3, 1, -1>(v, twr, q, two_q, 0u, zero);
-                    ct_half_stage<2, 1, -1>(v, twr, q, two_q, 0u, zero);
-                    ct_half_stage<1, 1, -1>(v, twr, q, two_q, 0u, zero);
-                    ct_half_stage<0, 1, -1>(v, twr, q, two_q, 0u, zero);
+                    ct_half_stage<4, 1, (L4 ? kB4 : -1)>(v, twr, q, two_q, four_q, zero);
+                    ct_half_stage<3, 1, (L4 ? kB3 : -1)>(v, twr, q, two_q, four_q, zero);
+                    ct_half_stage<2, 1, (L4 ? kB2 : -1)>(v, twr, q, two_q, four_q, zero);
+                    ct_half_stage<1, 1, (L4 ? kB1 : -1)>(v, twr, q, two_q, four_q, zero);
+                    ct_half_stage<0, 1, (L4 ? kB0 : -1)>(v, twr, q, two_q, four_q, zero);
                     if (j == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
                     team_sync(team);
                 }
@@ -557,8 +567,12 @@ tile_ct_kernel(const __grid_constant__ CUtensorMap map_lo, const __grid_constant
 #pragma unroll
                     for (int e = 0; e < 4; e++) {
                         uint32_t r = v[32 * h + 4 * c + e];
-                        r = min(r - two_q, r);
-                        o[e] = min(r - q, r);
+                        if (L4) {
+                            o[e] = canon_l4(kBRow, r, q, two_q, four_q);
+                        } else {
+                            r = min(r - two_q, r);
+                            o[e] = min(r - q, r);
+                        }
                     }
                     sts128(st_row + ((c << 4) ^ r1_xor), o[0], o[1], o[2], o[3]);
                 }
@@ -1230,6 +1244,7 @@ int multi_set_attrs() {
     NTTB200_CUDA(cudaFuncSetAttribute(tile_ct_kernel<true>, attr, kM_SmemBytes));
     NTTB200_CUDA(cudaFuncSetAttribute(tile_ct_kernel<false, false, false, true>, attr, kM_SmemBytesStaged));
     NTTB200_CUDA(cudaFuncSetAttribute(tile_ct_kernel<true, false, false, true>, attr, kM_SmemBytesStaged));
+    NTTB200_CUDA(cudaFuncSetAttribute(tile_ct_kernel<false, false, false, true, true>, attr, kM_SmemBytesStaged));
     NTTB200_CUDA(cudaFuncSetAttribute(tile_gs_kernel<false, false, 1>, attr, kM_SmemBytesTw));
     NTTB200_CUDA(cudaFuncSetAttribute(tile_gs_kernel<false, false, 2>, attr, kM_SmemBytesTw));
     NTTB200_CUDA(cudaFuncSetAttribute(tile_gs_kernel<true, false, 2>, attr, kM_SmemBytesTw));
@@ -1727,6 +1742,9 @@ int launch_multi_ct_mul(nttb200_plan *p, const int32_t *d_in, const int32_t *d_m
             tile_ct_kernel<false, true><<<tile_grid(p, tiles), kM_Threads, kM_SmemBytesTw, st>>>(
                 in_lo, in_hi, out_lo, out_hi, tp, kNoRns, in_lo, in_hi);
         }
+    } else if (ct_staged() && use_l4(p)) {
+        tile_ct_kernel<false, false, false, true, true><<<tile_grid(p, tiles), kM_Threads, kM_SmemBytesStaged, st>>>(
+            in_lo, in_hi, out_lo, out_hi, tp, kNoRns, in_lo, in_hi);
     } else if (ct_staged()) {
         tile_ct_kernel<false, false, false, true><<<tile_grid(p, tiles), kM_Threads, kM_SmemBytesStaged, st>>>(
             in_lo, in_hi, out_lo, out_hi, tp, kNoRns, in_lo, in_hi);
